@@ -1,0 +1,171 @@
+/*
+ * ifl_b200.h -- C ABI of libifl_b200.so, the B200 (sm_100a) implementation of the
+ * per-timestep hot path of tunabrain/incremental-fluids.
+ *
+ * The reference has no FFI: its boundary is the C++ class surface used by main()
+ * (FluidSolver::update / addInflow / toImage, FluidQuantity, SolidBody).  The
+ * drop-in classes in incremental-fluids_b200/host/ keep that surface and forward
+ * the bodies of the reference's PRIVATE hot-path methods to the entry points
+ * below.  Citations: vN:L == /root/reference/N-<chapter>/Fluid.cpp:L.
+ *
+ * Conventions
+ *  - one opaque ifl_ctx per FluidSolver; it owns every device buffer and one stream.
+ *  - host code never sees device pointers: arrays are addressed by ifl_buf ids and
+ *    moved with ifl_upload / ifl_download in the reference's dense row-major layout
+ *    (index x + y*w, v3:113-119); the physical device pitch is hidden.
+ *  - every function returns 0 on success, a negative IFL_E_* code otherwise
+ *    (ifl_last_error() gives the text).  There is NO CPU fallback: without a CUDA
+ *    device every compute entry point fails with IFL_E_CUDA.
+ *  - plain C types only.
+ */
+#ifndef IFL_B200_H
+#define IFL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ifl_ctx ifl_ctx;
+
+enum {
+    IFL_OK = 0,
+    IFL_E_ARG = -1,      /* bad argument / op not available for this chapter */
+    IFL_E_CUDA = -2,     /* CUDA runtime error or no device */
+    IFL_E_WATCHDOG = -3, /* an in-kernel dependency wait ran out (never expected) */
+    IFL_E_NOMEM = -4
+};
+
+/* Which chapter's update() semantics the context follows (1..8 == reference dirs). */
+typedef enum {
+    IFL_V1_MATRIXLESS = 1, /* GS project, Euler+bilinear advect   (1-matrixless)        */
+    IFL_V2_ADVECTION = 2,  /* GS project, RK3+Catmull-Rom          (2-better-advection)  */
+    IFL_V3_PCG = 3,        /* MIC(0)-PCG                           (3-conjugate-gradients)*/
+    IFL_V4_SOLIDS = 4,
+    IFL_V5_CURVED = 5,
+    IFL_V6_HEAT = 6,
+    IFL_V7_VARDENSITY = 7,
+    IFL_V8_FLIP = 8
+} ifl_version;
+
+/* Buffer ids.  Sizes (in elements, reference layout): cell-sized = w*h;
+ * u fields (w+1)*h; v fields w*(h+1).  All double unless noted. */
+typedef enum {
+    IFL_BUF_D_SRC = 0, /* FluidQuantity::_src of _d   v3:42  */
+    IFL_BUF_D_DST,     /* FluidQuantity::_dst of _d   v3:43  */
+    IFL_BUF_U_SRC,
+    IFL_BUF_U_DST,
+    IFL_BUF_V_SRC,
+    IFL_BUF_V_DST,
+    IFL_BUF_T_SRC, /* v6+ temperature v6:589 */
+    IFL_BUF_T_DST,
+    IFL_BUF_R,      /* FluidSolver::_r      v3:198 */
+    IFL_BUF_P,      /* FluidSolver::_p      v3:199 */
+    IFL_BUF_Z,      /* FluidSolver::_z      v3:200 */
+    IFL_BUF_S,      /* FluidSolver::_s      v3:201 */
+    IFL_BUF_PRECON, /* FluidSolver::_precon v3:202 */
+    IFL_BUF_ADIAG,  /* FluidSolver::_aDiag  v3:204 */
+    IFL_BUF_APLUSX, /* FluidSolver::_aPlusX v3:205 */
+    IFL_BUF_APLUSY, /* FluidSolver::_aPlusY v3:206 */
+    IFL_BUF_COUNT_
+} ifl_buf;
+
+/* Field ids for per-quantity ops (FluidQuantity instances of FluidSolver, v3:188-190). */
+typedef enum { IFL_FIELD_D = 0, IFL_FIELD_U = 1, IFL_FIELD_V = 2, IFL_FIELD_T = 3 } ifl_field;
+
+/* project() exit status; the host shim prints the reference's exact stdout line from it. */
+typedef enum {
+    IFL_SOLVE_CONVERGED = 0,     /* "Exiting solver after %d iterations, maximum error is %f"  v3:368 */
+    IFL_SOLVE_EXCEEDED = 1,      /* "Exceeded budget of %d iterations, maximum error was %f"   v3:379 */
+    IFL_SOLVE_INITIAL_SMALL = 2  /* early return, initial |r|inf < 1e-5                         v3:355 */
+} ifl_solve_status;
+
+typedef struct {
+    int status;       /* ifl_solve_status */
+    int iterations;   /* the zero-based `iter` the reference prints (v3:368), or `limit` when exceeded */
+    double max_error; /* |r|inf (PCG, v3:366) or max |delta p| (Gauss-Seidel, v2:262) at exit */
+} ifl_solve_info;
+
+/* ---- lifetime -------------------------------------------------------------- */
+/* FluidSolver ctor (v3:401-416): allocates fields + solver scratch on `device`,
+ * all zero, hx = 1/min(w,h). */
+int ifl_create(ifl_ctx **out, int w, int h, int version, int device);
+/* FluidSolver dtor (v3:418-431). */
+int ifl_destroy(ifl_ctx *ctx);
+const char *ifl_last_error(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long ifl_launch_count(const ifl_ctx *ctx);
+/* The CUDA stream (cudaStream_t as void*) every kernel of this context is launched on. */
+void *ifl_stream(const ifl_ctx *ctx);
+int ifl_sync(ifl_ctx *ctx);
+
+/* ---- measurement (bench.py's roofline leg) ------------------------------------ */
+/* Kernel classes of the hot path; per-class device time is measured with CUDA events
+ * recorded on the context's stream around every launch of that class. */
+typedef enum {
+    IFL_K_MATVEC = 0,   /* z = A s (+ z.s)                    v3:361-362 */
+    IFL_K_AXPY2_NORM,   /* p += a s; r -= a z; |r|inf         v3:363-366 */
+    IFL_K_PRECON_FWD,   /* forward substitution               v3:276-287 */
+    IFL_K_PRECON_BWD,   /* backward substitution (+ z.r)      v3:289-303, 374 */
+    IFL_K_XPAY,         /* s = z + b s                        v3:375 */
+    IFL_K_SCALAR,       /* alpha / convergence test / beta    */
+    IFL_K_FACTOR,       /* buildPreconditioner                v3:247-272 */
+    IFL_K_ASSEMBLY,     /* buildRhs, buildPressureMatrix, applyPressure, addInflow */
+    IFL_K_ADVECT,       /* FluidQuantity::advect              v2:170-183 */
+    IFL_K_GS_SWEEP,     /* one Gauss-Seidel sweep             v2:239-268 */
+    IFL_K_COUNT_
+} ifl_kernel_class;
+/* Start (on != 0) / stop per-class event timing; starting resets the accumulators. */
+int ifl_profile(ifl_ctx *ctx, int on);
+/* Synchronises the stream and returns accumulated device milliseconds and launch counts
+ * per class (arrays of IFL_K_COUNT_ entries). */
+int ifl_profile_read(ifl_ctx *ctx, double *ms, long long *launches);
+
+/* ---- data movement (backs FluidQuantity::at()/src(), toImage, test harness) ---- */
+size_t ifl_buf_elems(const ifl_ctx *ctx, int buf);
+int ifl_upload(ifl_ctx *ctx, int buf, const double *host);   /* dense host -> device   */
+int ifl_download(ifl_ctx *ctx, int buf, double *host);       /* device -> dense host   */
+int ifl_fill(ifl_ctx *ctx, int buf, double value);
+
+/* ---- FluidQuantity ops ------------------------------------------------------ */
+/* FluidQuantity::addInflow(x0,y0,x1,y1,v)  v2:188-205 (v1:141-151 when version==1),
+ * including the `_h`-for-`_w` clamp of the x loop. */
+int ifl_quantity_add_inflow(ifl_ctx *ctx, int field, double x0, double y0, double x1, double y1, double v);
+/* FluidQuantity::advect(timestep,u,v)  v2:170-183 (v1:125-138): src -> dst, reads u._src, v._src. */
+int ifl_advect(ifl_ctx *ctx, int field, double timestep);
+/* FluidQuantity::flip()  v3:105-107. */
+int ifl_flip(ifl_ctx *ctx, int field);
+
+/* ---- FluidSolver private hot-path methods ----------------------------------- */
+int ifl_build_rhs(ifl_ctx *ctx);                                         /* v3:208-217 */
+int ifl_build_pressure_matrix(ifl_ctx *ctx, double timestep, double density); /* v3:222-244 */
+int ifl_build_preconditioner(ifl_ctx *ctx);                              /* v3:247-272 */
+int ifl_apply_preconditioner(ifl_ctx *ctx, int dst, int a);              /* v3:275-304 */
+int ifl_matrix_vector_product(ifl_ctx *ctx, int dst, int b);             /* v3:315-332 */
+int ifl_dot_product(ifl_ctx *ctx, int a, int b, double *result);         /* v3:307-312 */
+int ifl_scaled_add(ifl_ctx *ctx, int dst, int a, int b, double s);       /* v3:335-338 */
+int ifl_infinity_norm(ifl_ctx *ctx, int a, double *result);              /* v3:341-346 */
+/* project(limit)  v3:349-380: MIC(0)-PCG, whole loop on the device. */
+int ifl_project(ifl_ctx *ctx, int limit, ifl_solve_info *info);
+/* project(limit, timestep)  v2:233-277 / v1:192-240: lexicographic Gauss-Seidel, warm-started _p. */
+int ifl_project_gs(ifl_ctx *ctx, int limit, double timestep, double density, ifl_solve_info *info);
+int ifl_apply_pressure(ifl_ctx *ctx, double timestep, double density);   /* v3:382-398 */
+
+/* ---- FluidSolver public surface --------------------------------------------- */
+/* FluidSolver::addInflow(x,y,w,h,d,u,v)  v3:449-453. */
+int ifl_add_inflow(ifl_ctx *ctx, double x, double y, double w, double h, double d, double u, double v);
+/* FluidSolver::update(timestep)  v3:433-447 (v2:320-332, v1:284-297): the whole
+ * step stays on the device.  `density` is the ctor's density; infos[0] receives
+ * the pressure solve's status (may be NULL). */
+int ifl_update(ifl_ctx *ctx, double timestep, double density, ifl_solve_info *infos);
+/* Same step with HOST buffers: uploads d,u,v (reference layout), runs update(),
+ * downloads d,u,v.  This is the end-to-end path bench.py times as `e2e`. */
+int ifl_update_host(ifl_ctx *ctx, double timestep, double density, double *d, double *u, double *v,
+                    ifl_solve_info *infos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFL_B200_H */

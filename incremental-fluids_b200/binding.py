@@ -1,0 +1,269 @@
+"""ctypes binding of libifl_b200.so and a Python mirror of the reference's FluidSolver.
+
+`FluidSolver` keeps the reference's method names and argument meaning
+(FluidSolver(w, h, density), addInflow, update, toImage; v3:401-466) and exposes the
+private hot-path methods (buildRhs, buildPressureMatrix, buildPreconditioner, project,
+applyPressure, ...) so that parity tests read like calls into the reference class.
+All compute happens in the CUDA library; there is no CPU fallback -- if the library
+or a CUDA device is missing, construction raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libifl_b200.so"
+
+
+class IflError(RuntimeError):
+    pass
+
+
+class SolveInfo(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int), ("iterations", ctypes.c_int), ("max_error", ctypes.c_double)]
+
+    def astuple(self):
+        return (self.status, self.iterations, self.max_error)
+
+
+# mirrors enum ifl_buf / ifl_field in include/ifl_b200.h
+BUF = {name: i for i, name in enumerate(
+    ["d.src", "d.dst", "u.src", "u.dst", "v.src", "v.dst", "t.src", "t.dst",
+     "r", "p", "z", "s", "precon", "aDiag", "aPlusX", "aPlusY"])}
+FIELD = {"d": 0, "u": 1, "v": 2, "t": 3}
+# mirrors enum ifl_kernel_class
+KERNEL_CLASSES = ["matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "scalar", "factor", "assembly",
+                  "advect", "gs_sweep"]
+
+EXPORTS = [
+    "ifl_create", "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
+    "ifl_profile", "ifl_profile_read",
+    "ifl_buf_elems", "ifl_upload", "ifl_download", "ifl_fill",
+    "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
+    "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
+    "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
+    "ifl_project", "ifl_project_gs", "ifl_apply_pressure",
+    "ifl_add_inflow", "ifl_update", "ifl_update_host",
+]
+
+
+def library_path():
+    return os.path.join(HERE, _LIB_NAME)
+
+
+def build_library(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libifl_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], stdout=out, stderr=out)
+    return library_path()
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise IflError(path + " is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = ctypes.CDLL(path)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    L.ifl_last_error.restype = ctypes.c_char_p
+    L.ifl_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci]
+    L.ifl_destroy.argtypes = [vp]
+    L.ifl_launch_count.restype = ctypes.c_longlong
+    L.ifl_launch_count.argtypes = [vp]
+    L.ifl_stream.restype = vp
+    L.ifl_stream.argtypes = [vp]
+    L.ifl_sync.argtypes = [vp]
+    L.ifl_profile.argtypes = [vp, ci]
+    L.ifl_profile_read.argtypes = [vp, vp, vp]
+    L.ifl_buf_elems.restype = ctypes.c_size_t
+    L.ifl_buf_elems.argtypes = [vp, ci]
+    L.ifl_upload.argtypes = [vp, ci, vp]
+    L.ifl_download.argtypes = [vp, ci, vp]
+    L.ifl_fill.argtypes = [vp, ci, cd]
+    L.ifl_quantity_add_inflow.argtypes = [vp, ci, cd, cd, cd, cd, cd]
+    L.ifl_advect.argtypes = [vp, ci, cd]
+    L.ifl_flip.argtypes = [vp, ci]
+    L.ifl_build_rhs.argtypes = [vp]
+    L.ifl_build_pressure_matrix.argtypes = [vp, cd, cd]
+    L.ifl_build_preconditioner.argtypes = [vp]
+    L.ifl_apply_preconditioner.argtypes = [vp, ci, ci]
+    L.ifl_matrix_vector_product.argtypes = [vp, ci, ci]
+    L.ifl_dot_product.argtypes = [vp, ci, ci, ctypes.POINTER(cd)]
+    L.ifl_scaled_add.argtypes = [vp, ci, ci, ci, cd]
+    L.ifl_infinity_norm.argtypes = [vp, ci, ctypes.POINTER(cd)]
+    L.ifl_project.argtypes = [vp, ci, ctypes.POINTER(SolveInfo)]
+    L.ifl_project_gs.argtypes = [vp, ci, cd, cd, ctypes.POINTER(SolveInfo)]
+    L.ifl_apply_pressure.argtypes = [vp, cd, cd]
+    L.ifl_add_inflow.argtypes = [vp, cd, cd, cd, cd, cd, cd, cd]
+    L.ifl_update.argtypes = [vp, cd, cd, ctypes.POINTER(SolveInfo)]
+    L.ifl_update_host.argtypes = [vp, cd, cd, vp, vp, vp, ctypes.POINTER(SolveInfo)]
+    _lib = L
+    return L
+
+
+class FluidSolver:
+    """Drop-in mirror of the reference's FluidSolver for chapters 1-3.
+
+    FluidSolver(w, h, density)                    v3:401
+    addInflow(x, y, w, h, d, u, v)                v3:449
+    update(timestep)                              v3:433
+    toImage() -> uint8[h*w*4]                     v3:455
+    """
+
+    def __init__(self, w, h, density, version=3, device=0):
+        self.L = load_library()
+        self.w, self.h, self.density, self.version = w, h, density, version
+        self.hx = 1.0 / min(w, h)
+        ctx = ctypes.c_void_p()
+        self.ctx = None
+        self._chk(self.L.ifl_create(ctypes.byref(ctx), w, h, version, device))
+        self.ctx = ctx
+        self.last = None
+        self.messages = []  # the stdout lines the reference would have printed
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise IflError("libifl_b200 error %d: %s" % (rc, self.L.ifl_last_error().decode()))
+
+    def close(self):
+        if self.ctx is not None:
+            self.L.ifl_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data access (FluidQuantity::src()/at(), and the solver's private arrays)
+    def get(self, name):
+        n = self.L.ifl_buf_elems(self.ctx, BUF[name])
+        if n == 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        self._chk(self.L.ifl_download(self.ctx, BUF[name], out.ctypes.data))
+        return out
+
+    def set(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).ravel()
+        if a.size != self.L.ifl_buf_elems(self.ctx, BUF[name]):
+            raise ValueError("size mismatch for " + name)
+        self._chk(self.L.ifl_upload(self.ctx, BUF[name], a.ctypes.data))
+
+    def launches(self):
+        return self.L.ifl_launch_count(self.ctx)
+
+    def stream(self):
+        return self.L.ifl_stream(self.ctx)
+
+    def sync(self):
+        self._chk(self.L.ifl_sync(self.ctx))
+
+    def profile(self, on=True):
+        self._chk(self.L.ifl_profile(self.ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel class: (device ms, launches)} accumulated since profile(True)."""
+        ms = np.zeros(len(KERNEL_CLASSES))
+        n = np.zeros(len(KERNEL_CLASSES), dtype=np.int64)
+        self._chk(self.L.ifl_profile_read(self.ctx, ms.ctypes.data, n.ctypes.data))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    # ---- private hot-path methods of the reference class
+    def buildRhs(self):
+        self._chk(self.L.ifl_build_rhs(self.ctx))
+
+    def buildPressureMatrix(self, timestep):
+        self._chk(self.L.ifl_build_pressure_matrix(self.ctx, timestep, self.density))
+
+    def buildPreconditioner(self):
+        self._chk(self.L.ifl_build_preconditioner(self.ctx))
+
+    def applyPreconditioner(self, dst, a):
+        self._chk(self.L.ifl_apply_preconditioner(self.ctx, BUF[dst], BUF[a]))
+
+    def matrixVectorProduct(self, dst, b):
+        self._chk(self.L.ifl_matrix_vector_product(self.ctx, BUF[dst], BUF[b]))
+
+    def dotProduct(self, a, b):
+        out = ctypes.c_double()
+        self._chk(self.L.ifl_dot_product(self.ctx, BUF[a], BUF[b], ctypes.byref(out)))
+        return out.value
+
+    def scaledAdd(self, dst, a, b, s):
+        self._chk(self.L.ifl_scaled_add(self.ctx, BUF[dst], BUF[a], BUF[b], s))
+
+    def infinityNorm(self, a):
+        out = ctypes.c_double()
+        self._chk(self.L.ifl_infinity_norm(self.ctx, BUF[a], ctypes.byref(out)))
+        return out.value
+
+    def _message(self, info, gs):
+        what = "change" if gs else "error"
+        if info.status == 0:
+            return "Exiting solver after %d iterations, maximum %s is %f" % (info.iterations, what, info.max_error)
+        if info.status == 1:
+            return "Exceeded budget of %d iterations, maximum %s was %f" % (info.iterations, what, info.max_error)
+        return None  # v3:355-356 returns silently
+
+    def project(self, limit, timestep=None):
+        info = SolveInfo()
+        if self.version >= 3:
+            self._chk(self.L.ifl_project(self.ctx, limit, ctypes.byref(info)))
+        else:
+            self._chk(self.L.ifl_project_gs(self.ctx, limit, timestep, self.density, ctypes.byref(info)))
+        self._record(info)
+        return self.last
+
+    def _record(self, info):
+        self.last = info.astuple()
+        msg = self._message(info, self.version < 3)
+        if msg:
+            self.messages.append(msg)
+
+    def applyPressure(self, timestep):
+        self._chk(self.L.ifl_apply_pressure(self.ctx, timestep, self.density))
+
+    def advect(self, field, timestep):
+        self._chk(self.L.ifl_advect(self.ctx, FIELD[field], timestep))
+
+    def flip(self, field):
+        self._chk(self.L.ifl_flip(self.ctx, FIELD[field]))
+
+    def quantityAddInflow(self, field, x0, y0, x1, y1, v):
+        self._chk(self.L.ifl_quantity_add_inflow(self.ctx, FIELD[field], x0, y0, x1, y1, v))
+
+    # ---- public surface
+    def addInflow(self, x, y, w, h, d, u, v):
+        self._chk(self.L.ifl_add_inflow(self.ctx, x, y, w, h, d, u, v))
+
+    def update(self, timestep):
+        info = SolveInfo()
+        self._chk(self.L.ifl_update(self.ctx, timestep, self.density, ctypes.byref(info)))
+        self._record(info)
+        return self.last
+
+    def update_host(self, timestep, d, u, v):
+        """update() on HOST arrays (in/out, reference layout): H2D + step + D2H."""
+        info = SolveInfo()
+        self._chk(self.L.ifl_update_host(self.ctx, timestep, self.density, d.ctypes.data, u.ctypes.data,
+                                         v.ctypes.data, ctypes.byref(info)))
+        self._record(info)
+        return self.last
+
+    def toImage(self):
+        d = self.get("d.src")
+        shade = ((1.0 - d) * 255.0).astype(np.int64)  # (int) truncation, v3:457
+        shade = np.maximum(np.minimum(shade, 255), 0).astype(np.uint8)
+        rgba = np.empty((d.size, 4), dtype=np.uint8)
+        rgba[:, 0] = rgba[:, 1] = rgba[:, 2] = shade
+        rgba[:, 3] = 0xFF
+        return rgba.ravel()

@@ -1,0 +1,157 @@
+// assembly_kernels.cu -- pressure-system assembly and application, inflow stamping.
+//
+//   build_rhs        FluidSolver::buildRhs            v3:208-217
+//   build_matrix     FluidSolver::buildPressureMatrix v3:222-244
+//   apply_pressure   FluidSolver::applyPressure       v3:382-398
+//   add_inflow       FluidQuantity::addInflow         v2:188-205 / v1:141-151
+//
+// The reference writes these as scatter loops in raster order.  Here each output
+// element is owned by one thread (gather form); the floating-point additions are
+// issued in the order in which the reference's scatter would have ARRIVED at that
+// element, so results are bit-identical.
+// All kernels are HBM-streaming pointwise kernels: one thread per element,
+// x fastest, 256-thread blocks covering a 128x2... rows of the pitched arrays.
+#include "ifl_internal.cuh"
+
+namespace ifl {
+
+// r = -(1/hx) * (u[x+1,y] - u[x,y] + v[x,y+1] - v[x,y])            v3:213-214
+__global__ void __launch_bounds__(256) k_build_rhs(Arr r, Arr u, Arr v, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= r.w || y >= r.h) return;
+    const double ul = u.p[x + (size_t)y * u.pitch];
+    const double ur = u.p[x + 1 + (size_t)y * u.pitch];
+    const double vt = v.p[x + (size_t)y * v.pitch];
+    const double vb = v.p[x + (size_t)(y + 1) * v.pitch];
+    r.p[x + (size_t)y * r.pitch] = -scale * (ur - ul + vb - vt);
+}
+
+// Gather form of v3:227-243.  aDiag[idx] receives, in raster order of the scattering
+// cell: +scale from the cell above (its y-branch), +scale from the cell to the left
+// (its x-branch), then the cell's own x-branch and y-branch.
+__global__ void __launch_bounds__(256) k_build_matrix(Arr aDiag, Arr aPlusX, Arr aPlusY, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int w = aDiag.w, h = aDiag.h;
+    if (x >= w || y >= h) return;
+    double diag = 0.0;
+    if (y > 0) diag += scale;
+    if (x > 0) diag += scale;
+    double ax = 0.0, ay = 0.0;
+    if (x < w - 1) {
+        diag += scale;
+        ax = -scale;
+    }
+    if (y < h - 1) {
+        diag += scale;
+        ay = -scale;
+    }
+    const size_t i = x + (size_t)y * aDiag.pitch;
+    aDiag.p[i] = diag;
+    aPlusX.p[i] = ax;
+    aPlusY.p[i] = ay;
+}
+
+// u face (x,y), x in [0,W]: receives "+= scale*p[x-1,y]" (cell x-1, visited first)
+// and then "-= scale*p[x,y]" (cell x).  v3:387-388; wall faces zeroed v3:394-395.
+__global__ void __launch_bounds__(256) k_apply_pressure_u(Arr u, Arr p, double scale, int zero_walls) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int W = p.w;
+    if (x > W || y >= u.h) return;
+    const size_t iu = x + (size_t)y * u.pitch;
+    double val = u.p[iu];
+    if (x > 0) val += scale * p.p[x - 1 + (size_t)y * p.pitch];
+    if (x < W) val -= scale * p.p[x + (size_t)y * p.pitch];
+    if (zero_walls && (x == 0 || x == W)) val = 0.0;
+    u.p[iu] = val;
+}
+
+// v face (x,y), y in [0,H]: "+= scale*p[x,y-1]" then "-= scale*p[x,y]".  v3:389-390, 396-397.
+__global__ void __launch_bounds__(256) k_apply_pressure_v(Arr v, Arr p, double scale, int zero_walls) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int H = p.h;
+    if (x >= v.w || y > H) return;
+    const size_t iv = x + (size_t)y * v.pitch;
+    double val = v.p[iv];
+    if (y > 0) val += scale * p.p[x + (size_t)(y - 1) * p.pitch];
+    if (y < H) val -= scale * p.p[x + (size_t)y * p.pitch];
+    if (zero_walls && (y == 0 || y == H)) val = 0.0;
+    v.p[iv] = val;
+}
+
+// FluidQuantity::addInflow.  The reference clamps the x loop with _h, not _w
+// (v2:195) -- kept.  smooth==0 is chapter 1's hard-edged
+// stamp (v1:147-150), smooth==1 the cubic-pulse blob (v2:196-202).
+__global__ void k_add_inflow(Arr src, int ix_lo, int ix_hi, int iy_lo, int iy_hi, double hx, double x0,
+                             double y0, double x1, double y1, double v, int smooth) {
+    const int x = ix_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = iy_lo + blockIdx.y;
+    if (x >= ix_hi || y >= iy_hi) return;
+    double vi = v;
+    if (smooth) {
+        const double lx = (2.0 * (x + 0.5) * hx - (x0 + x1)) / (x1 - x0);
+        const double ly = (2.0 * (y + 0.5) * hx - (y0 + y1)) / (y1 - y0);
+        const double l = sqrt(lx * lx + ly * ly); // length() v2:33
+        const double xx = std_min(fabs(l), 1.0);   // cubicPulse() v2:42-45
+        vi = (1.0 - xx * xx * (3.0 - 2.0 * xx)) * v;
+    }
+    const size_t i = x + (size_t)y * src.pitch;
+    if (fabs(src.p[i]) < fabs(vi)) src.p[i] = vi;
+}
+
+static dim3 grid2d(int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); }
+
+int launch_build_rhs(ifl_ctx *c) {
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double scale = 1.0 / c->hx;
+    k_build_rhs<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_U].src, c->fd[IFL_FIELD_V].src,
+                                                            scale);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double scale = timestep / (density * c->hx * c->hx);
+    k_build_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double scale = timestep / (density * c->hx);
+    Field &u = c->fd[IFL_FIELD_U], &v = c->fd[IFL_FIELD_V];
+    k_apply_pressure_u<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, scale, 1);
+    IFL_LAUNCHED(c);
+    k_apply_pressure_v<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, scale, 1);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_add_inflow(ifl_ctx *c, int field, double x0, double y0, double x1, double y1, double v) {
+    Field &f = c->fd[field];
+    // v2:189-192 -- truncating casts, evaluated on the host exactly as the reference does
+    const int ix0 = (int)(x0 / c->hx - f.ox);
+    const int iy0 = (int)(y0 / c->hx - f.oy);
+    const int ix1 = (int)(x1 / c->hx - f.ox);
+    const int iy1 = (int)(y1 / c->hx - f.oy);
+    const int xlo = imax(ix0, 0), xhi = imin(ix1, f.h); // sic: _h (v2:195)
+    const int ylo = imax(iy0, 0), yhi = imin(iy1, f.h);
+    if (xhi <= xlo || yhi <= ylo) return IFL_OK;
+    if (xhi > f.src.pitch) { // only reachable on w < h grids, where the reference itself reads out of row
+        set_error("addInflow: x range [%d,%d) exceeds the row pitch on a w<h grid", xlo, xhi);
+        return IFL_E_ARG;
+    }
+    dim3 grid((xhi - xlo + 127) / 128, yhi - ylo);
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    k_add_inflow<<<grid, 128, 0, c->stream>>>(f.src, xlo, xhi, ylo, yhi, c->hx, x0, y0, x1, y1, v,
+                                              c->version >= 2 ? 1 : 0);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+} // namespace ifl

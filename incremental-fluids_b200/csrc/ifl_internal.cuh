@@ -1,0 +1,181 @@
+// ifl_internal.cuh -- shared declarations of libifl_b200 (device context, array
+// descriptors, exact-arithmetic helpers, deterministic block reductions).
+//
+// Arithmetic contract: every kernel in this library must reproduce the reference's
+// double-precision results operation by operation.  The whole library is compiled
+// with -fmad=false (no contraction), and helpers below restate std::min/std::max
+// with the libstdc++ tie/NaN/-0.0 behaviour instead of fmin/fmax.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ifl_b200.h"
+
+namespace ifl {
+
+// ------------------------------------------------------------------ layout ----
+// Every array lives in HBM as a pitched 2-D block: logical w x h, physical
+// pitch = round_up(w, 32) elements, rows = round_up(h, 32) + 32.  Pad cells are
+// zero forever (kernels never store outside x<w, y<h), which lets tile loaders
+// (cp.async.bulk needs 16-byte aligned 16-byte multiples) fetch full 32-wide tiles
+// at any grid size.  The reference's dense x + y*w layout exists only on the host
+// side of ifl_upload/ifl_download.
+constexpr int TILE = 32;
+
+struct Arr {
+    double *p;
+    int w, h, pitch, rows;
+    __host__ __device__ size_t bytes() const { return (size_t)pitch * rows * sizeof(double); }
+};
+
+struct Field { // one FluidQuantity (v3:41-49)
+    Arr src, dst;
+    int w, h;
+    double ox, oy;
+};
+
+// Device-resident scalars of one PCG / Gauss-Seidel solve (no host round trips
+// inside the loop; the host only reads `done`/`iter` through a pinned mirror).
+struct SolveScalars {
+    double sigma;     // z.r          v3:358
+    double alpha;     // sigma/(z.s)  v3:362
+    double beta;      // sigmaNew/sigma v3:375
+    double max_error; // |r|inf       v3:366
+    int iter;         // zero-based iteration counter (what v3:368 prints)
+    int done;         // 0 running, 1 converged, 2 initial-small
+    int watchdog;     // set by a dependency wait that ran out
+    int pad;
+};
+
+constexpr int MAX_PARTIALS = 8192; // per-block partial results of one reduction
+
+} // namespace ifl
+
+struct ifl_ctx {
+    int W, H, version, device;
+    double hx;
+    cudaStream_t stream;
+    ifl::Field fd[4]; // d, u, v, t
+    ifl::Arr r, p, z, s, q, precon, aDiag, aPlusX, aPlusY, cx, cy;
+    double *partials;          // [MAX_PARTIALS] block partials (sum or max)
+    int n_partials;            // valid entries written by the last reducing kernel
+    ifl::SolveScalars *scal;   // device
+    ifl::SolveScalars *scal_h; // pinned host mirror
+    double *result_h;          // pinned 8 doubles for scalar results
+    // wavefront sweep plumbing (sweep_kernels.cu)
+    unsigned long long *handoff; // [strips][pitch] x {value bits, epoch}
+    unsigned long long *ticket;  // strip ticket counter
+    unsigned long long epoch;    // last used handoff epoch
+    int n_strips;
+    unsigned long long sweep_launches; // sweeps launched so far (ticket base = launches * strips)
+    long long launches;
+    // per-kernel-class event timing (ifl_profile): ring of (start, stop, class)
+    int prof_on;
+    int prof_head, prof_count; // oldest pending pair, number of pending pairs
+    cudaEvent_t *prof_ev;      // [2 * PROF_RING]
+    int *prof_cls;             // [PROF_RING]
+    double prof_ms[IFL_K_COUNT_];
+    long long prof_n[IFL_K_COUNT_];
+};
+
+namespace ifl {
+
+// -------------------------------------------------------------- error plumbing --
+void set_error(const char *fmt, ...);
+#define IFL_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            ifl::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return IFL_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+#define IFL_LAUNCHED(ctx)                                                                      \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess) {                                                               \
+            ifl::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return IFL_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------- profiling --
+constexpr int PROF_RING = 4096;
+void prof_begin(ifl_ctx *c, int cls);
+void prof_end(ifl_ctx *c);
+struct ProfScope { // brackets one kernel launch with events when profiling is on
+    ifl_ctx *c;
+    ProfScope(ifl_ctx *ctx, int cls) : c(ctx) {
+        if (c->prof_on) prof_begin(c, cls);
+    }
+    ~ProfScope() {
+        if (c->prof_on) prof_end(c);
+    }
+};
+
+// ------------------------------------------------------------ exact arithmetic --
+// std::min(a,b) == (b < a) ? b : a ; std::max(a,b) == (a < b) ? b : a   (libstdc++)
+__host__ __device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
+__host__ __device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
+__host__ __device__ __forceinline__ int imin(int a, int b) { return (b < a) ? b : a; }
+__host__ __device__ __forceinline__ int imax(int a, int b) { return (a < b) ? b : a; }
+
+// ------------------------------------------------- deterministic block reductions --
+// Fixed-shape trees (xor-shuffle inside the warp, then a fixed loop over warps), so a
+// given grid configuration always produces the same bits.
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = std_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// All threads must call; result valid in thread 0.  `red` = shared double[32].
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+        t = red[0];
+        for (int i = 1; i < nw; i++) t = IS_MAX ? std_max(t, red[i]) : (t + red[i]);
+    }
+    __syncthreads();
+    return t;
+}
+#endif
+
+// ------------------------------------------------------------ kernel entry points --
+// pcg_kernels.cu
+int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot);
+int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b);
+int launch_scaled_add(ifl_ctx *c, const Arr &dst, const Arr &a, const Arr &b, double s);
+int launch_inf_norm(ifl_ctx *c, const Arr &a);
+int launch_finish_reduce(ifl_ctx *c, bool is_max, double *out_dev);
+int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info);
+// sweep_kernels.cu
+int sweep_init(ifl_ctx *c);
+void sweep_free(ifl_ctx *c);
+int launch_mic0_factor(ifl_ctx *c);
+int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
+int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
+int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
+// assembly_kernels.cu
+int launch_build_rhs(ifl_ctx *c);
+int launch_build_matrix(ifl_ctx *c, double timestep, double density);
+int launch_apply_pressure(ifl_ctx *c, double timestep, double density);
+int launch_add_inflow(ifl_ctx *c, int field, double x0, double y0, double x1, double y1, double v);
+// advect_kernels.cu
+int launch_advect(ifl_ctx *c, int field, double timestep);
+
+} // namespace ifl

@@ -1,0 +1,407 @@
+// pcg_kernels.cu -- the HBM-streaming half of the MIC(0)-PCG loop and its driver.
+//
+//   k_matvec       FluidSolver::matrixVectorProduct v3:315-332 (+ fused dotProduct(z,s) v3:362)
+//   k_axpy2_norm   scaledAdd x2 + infinityNorm       v3:363-366
+//   k_xpay         scaledAdd(s, z, s, beta)           v3:375
+//   k_dot / k_inf_norm / k_scaled_add                 v3:307-312, 341-346, 335-338 (granular ABI)
+//   k_scalar<...>  the three global scalars of an iteration (alpha, |r|inf test, beta)
+//   pcg_project    FluidSolver::project(limit)        v3:349-380
+//
+// Layout: pitched arrays (ifl_internal.cuh).  Every thread owns an x-pair (one
+// 16-byte double2 per array per row) and walks ROWS_PER_THREAD consecutive rows, so
+// the stencil keeps the rows above/below in registers (each array is read once from
+// HBM; x-neighbours come from warp shuffles).  Reductions are two-level and
+// deterministic: fixed tree inside the block -> partials[block] -> one finishing
+// block that sums the partials in a fixed order.
+//
+// The vector that receives A*s is a separate buffer `q` (the reference reuses _z,
+// v3:361); this only renames storage and lets s = z + beta*s be fused into later
+// kernels without a read-after-write hazard.  ifl_download(IFL_BUF_Z) is unaffected.
+#include "ifl_internal.cuh"
+
+#include <string.h>
+
+namespace ifl {
+
+constexpr int VEC_THREADS = 128;                // x-pairs per block -> 256 columns
+constexpr int VEC_COLS = VEC_THREADS * 2;
+constexpr int VEC_ROWS = 16;                    // rows walked by each thread
+
+static dim3 vec_grid(const Arr &a) { return dim3((a.w + VEC_COLS - 1) / VEC_COLS, (a.h + VEC_ROWS - 1) / VEC_ROWS); }
+static int vec_blocks(const Arr &a) {
+    dim3 g = vec_grid(a);
+    return (int)(g.x * g.y);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+// dst = A*b (5-point stencil in the reference's summation order: diag, left, up,
+// right, down); optionally partial[block] = sum(dst*b) over the block's cells.
+template <bool WITH_DOT>
+__global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDiag, Arr aPlusX, Arr aPlusY,
+                                                         double *__restrict__ partials,
+                                                         const SolveScalars *__restrict__ gate) {
+    if (gate && gate->done) return;
+    __shared__ double red[32];
+    const int W = dst.w, H = dst.h, pitch = dst.pitch;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
+    const int y0 = blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, H);
+    const bool in = x < pitch; // may load (pad columns are zero)
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    // rolling registers: b and aPlusY of the row above, b of this row and the row below
+    double2 b_up = zero2, ay_up = zero2, b_c = zero2, b_dn;
+    if (in) {
+        if (y0 > 0) {
+            b_up = ld2(b.p + x + (size_t)(y0 - 1) * pitch);
+            ay_up = ld2(aPlusY.p + x + (size_t)(y0 - 1) * pitch);
+        }
+        b_c = ld2(b.p + x + (size_t)y0 * pitch);
+    }
+    double acc = 0.0;
+    for (int y = y0; y < y1; y++) {
+        const size_t row = (size_t)y * pitch;
+        double2 ad = zero2, ax = zero2, ay = zero2;
+        b_dn = zero2;
+        if (in) {
+            ad = ld2(aDiag.p + x + row);
+            ax = ld2(aPlusX.p + x + row);
+            ay = ld2(aPlusY.p + x + row);
+            b_dn = ld2(b.p + x + row + pitch); // rows >= H are zero pad (allocation has 32 spare rows)
+        }
+        // x-neighbours: b[x-1], aPlusX[x-1] from the lane to the left, b[x+2] from the right
+        double b_l = __shfl_up_sync(0xffffffffu, b_c.y, 1);
+        double ax_l = __shfl_up_sync(0xffffffffu, ax.y, 1);
+        double b_r = __shfl_down_sync(0xffffffffu, b_c.x, 1);
+        if (lane == 0 && x > 0 && in) {
+            b_l = b.p[x - 1 + row];
+            ax_l = aPlusX.p[x - 1 + row];
+        }
+        if (lane == 31 && x + 2 < pitch) b_r = b.p[x + 2 + row];
+
+        // cell x
+        double t0 = ad.x * b_c.x;
+        if (x > 0) t0 += ax_l * b_l;
+        if (y > 0) t0 += ay_up.x * b_up.x;
+        if (x < W - 1) t0 += ax.x * b_c.y;
+        if (y < H - 1) t0 += ay.x * b_dn.x;
+        // cell x+1
+        double t1 = ad.y * b_c.y;
+        t1 += ax.x * b_c.x; // x+1 > 0 always
+        if (y > 0) t1 += ay_up.y * b_up.y;
+        if (x + 1 < W - 1) t1 += ax.y * b_r;
+        if (y < H - 1) t1 += ay.y * b_dn.y;
+
+        if (x + 1 < W) {
+            st2(dst.p + x + row, make_double2(t0, t1));
+            if (WITH_DOT) {
+                acc += t0 * b_c.x;
+                acc += t1 * b_c.y;
+            }
+        } else if (x < W) {
+            dst.p[x + row] = t0;
+            if (WITH_DOT) acc += t0 * b_c.x;
+        }
+        b_up = b_c;
+        b_c = b_dn;
+        ay_up = ay;
+    }
+    if (WITH_DOT) {
+        const double s = block_reduce<false>(acc, red);
+        if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// p += alpha*s ; r += q*(-alpha) ; partial[block] = max|r|     v3:363-366
+__global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r, Arr q, const SolveScalars *sc,
+                                                             double *__restrict__ partials) {
+    if (sc->done) return;
+    __shared__ double red[32];
+    const double alpha = sc->alpha;
+    const double nalpha = -alpha;
+    const int W = p.w, H = p.h, pitch = p.pitch;
+    const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
+    const int y0 = blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, H);
+    double m = 0.0;
+    if (x < W) {
+#pragma unroll 4
+        for (int y = y0; y < y1; y++) {
+            const size_t i = x + (size_t)y * pitch;
+            double2 pv = ld2(p.p + i), sv = ld2(s.p + i), rv = ld2(r.p + i), qv = ld2(q.p + i);
+            pv.x = pv.x + sv.x * alpha;
+            pv.y = pv.y + sv.y * alpha;
+            rv.x = rv.x + qv.x * nalpha;
+            rv.y = rv.y + qv.y * nalpha;
+            st2(p.p + i, pv);
+            st2(r.p + i, rv);
+            m = std_max(m, fabs(rv.x));
+            m = std_max(m, fabs(rv.y)); // pad column (x+1 == W) holds 0 -> no effect
+        }
+    }
+    m = block_reduce<true>(m, red);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = m;
+}
+
+// dst = a + b*scale, scale either immediate or read from the device scalars (beta)
+template <bool BETA_FROM_SCALARS>
+__global__ void __launch_bounds__(VEC_THREADS) k_scaled_add(Arr dst, Arr a, Arr b, double scale,
+                                                             const SolveScalars *sc) {
+    if (BETA_FROM_SCALARS) {
+        if (sc->done) return;
+        scale = sc->beta;
+    }
+    const int W = dst.w, H = dst.h, pitch = dst.pitch;
+    const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
+    const int y0 = blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, H);
+    if (x >= W) return;
+#pragma unroll 4
+    for (int y = y0; y < y1; y++) {
+        const size_t i = x + (size_t)y * pitch;
+        const double2 av = ld2(a.p + i), bv = ld2(b.p + i);
+        st2(dst.p + i, make_double2(av.x + bv.x * scale, av.y + bv.y * scale));
+    }
+}
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *__restrict__ partials) {
+    __shared__ double red[32];
+    const int W = a.w, H = a.h, pitch = a.pitch;
+    const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
+    const int y0 = blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, H);
+    double acc = 0.0;
+    if (x < W) {
+        for (int y = y0; y < y1; y++) {
+            const size_t i = x + (size_t)y * pitch;
+            const double2 av = ld2(a.p + i);
+            if (IS_MAX) {
+                acc = std_max(acc, fabs(av.x));
+                acc = std_max(acc, fabs(av.y));
+            } else {
+                const double2 bv = ld2(b.p + i);
+                acc += av.x * bv.x;
+                acc += av.y * bv.y;
+            }
+        }
+    }
+    acc = block_reduce<IS_MAX>(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// ---- scalar stage: one block folds the partials in a fixed order and updates the
+// solve scalars.  MODE: 0 alpha = sigma/sum ; 1 convergence test on max ; 2 beta,
+// sigma, iter++ ; 3 sigma = sum (prologue) ; 4 initial test (done=2 if small) ;
+// 5 plain store of the reduced value to out[0].
+enum { SC_ALPHA = 0, SC_CHECK = 1, SC_BETA = 2, SC_SIGMA0 = 3, SC_CHECK0 = 4, SC_STORE = 5 };
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_scalar(const double *__restrict__ partials, int n, SolveScalars *sc,
+                                                  double *out) {
+    constexpr bool IS_MAX = (MODE == SC_CHECK || MODE == SC_CHECK0);
+    if (MODE != SC_STORE && MODE != SC_SIGMA0 && MODE != SC_CHECK0 && sc->done) return;
+    __shared__ double red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) v = IS_MAX ? std_max(v, partials[i]) : (v + partials[i]);
+    v = block_reduce<IS_MAX>(v, red);
+    if (threadIdx.x != 0) return;
+    if (MODE == SC_ALPHA) {
+        sc->alpha = sc->sigma / v; // v3:362
+    } else if (MODE == SC_CHECK) {
+        sc->max_error = v;
+        if (v < 1e-5) sc->done = 1; // v3:367
+    } else if (MODE == SC_BETA) {
+        sc->beta = v / sc->sigma; // v3:375
+        sc->sigma = v;            // v3:376
+        sc->iter = sc->iter + 1;
+    } else if (MODE == SC_SIGMA0) {
+        sc->sigma = v; // v3:358
+    } else if (MODE == SC_CHECK0) {
+        sc->max_error = v;
+        if (v < 1e-5) sc->done = 2; // v3:355
+    } else {
+        out[0] = v;
+    }
+}
+
+// ------------------------------------------------------------------ launchers ----
+
+
+int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
+    ProfScope ps_(c, IFL_K_MATVEC);
+    dim3 g = vec_grid(dst);
+    if (with_dot) {
+        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, c->partials, c->scal);
+        c->n_partials = vec_blocks(dst);
+    } else {
+        k_matvec<false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, nullptr, nullptr);
+    }
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
+    ProfScope ps_(c, IFL_K_SCALAR);
+    k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, c->partials);
+    c->n_partials = vec_blocks(a);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_inf_norm(ifl_ctx *c, const Arr &a) {
+    ProfScope ps_(c, IFL_K_SCALAR);
+    k_reduce2<true><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, a, c->partials);
+    c->n_partials = vec_blocks(a);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_scaled_add(ifl_ctx *c, const Arr &dst, const Arr &a, const Arr &b, double s) {
+    ProfScope ps_(c, IFL_K_XPAY);
+    k_scaled_add<false><<<vec_grid(dst), VEC_THREADS, 0, c->stream>>>(dst, a, b, s, nullptr);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+__global__ void __launch_bounds__(1024) k_store_max(const double *__restrict__ partials, int n, double *out) {
+    __shared__ double red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) v = std_max(v, partials[i]);
+    v = block_reduce<true>(v, red);
+    if (threadIdx.x == 0) out[0] = v;
+}
+
+// Folds the partials of the last reducing kernel into out_dev[0] (granular ABI ops).
+int launch_finish_reduce(ifl_ctx *c, bool is_max, double *out_dev) {
+    ProfScope ps_(c, IFL_K_SCALAR);
+    if (is_max)
+        k_store_max<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, out_dev);
+    else
+        k_scalar<SC_STORE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, out_dev);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+template <int MODE>
+static int scalar_stage(ifl_ctx *c) {
+    ProfScope ps_(c, IFL_K_SCALAR);
+    k_scalar<MODE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, nullptr);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+#define IFL_TRY(expr)            \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != IFL_OK) return rc_; \
+    } while (0)
+
+// One PCG iteration, enqueued without any host synchronisation (v3:361-376).
+static int enqueue_iteration(ifl_ctx *c) {
+    IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
+    IFL_TRY(scalar_stage<SC_ALPHA>(c));
+    {
+        ProfScope ps_(c, IFL_K_AXPY2_NORM);
+        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, c->partials);
+        c->n_partials = vec_blocks(c->p);
+        IFL_LAUNCHED(c);
+    }
+    IFL_TRY(scalar_stage<SC_CHECK>(c));
+    IFL_TRY(launch_precon_forward(c, c->z, c->r, true));
+    IFL_TRY(launch_precon_backward(c, c->z, c->r, true, true)); // partial z.r
+    IFL_TRY(scalar_stage<SC_BETA>(c));
+    {
+        ProfScope ps_(c, IFL_K_XPAY);
+        k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal);
+        IFL_LAUNCHED(c);
+    }
+    return IFL_OK;
+}
+
+int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
+    cudaStream_t st = c->stream;
+    // prologue v3:350-358
+    IFL_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScalars), st));
+    IFL_CUDA(cudaMemsetAsync(c->p.p, 0, c->p.bytes(), st));
+    IFL_TRY(launch_precon_forward(c, c->z, c->r, false));
+    IFL_TRY(launch_precon_backward(c, c->z, c->r, true, false));
+    IFL_TRY(scalar_stage<SC_SIGMA0>(c));
+    IFL_CUDA(cudaMemcpyAsync(c->s.p, c->z.p, c->z.bytes(), cudaMemcpyDeviceToDevice, st));
+    IFL_TRY(launch_inf_norm(c, c->r));
+    IFL_TRY(scalar_stage<SC_CHECK0>(c));
+
+    // The host looks at the solve scalars only through a pinned mirror and only
+    // BETWEEN chunks of iterations, never inside one.  Every kernel of an iteration is
+    // gated on scal->done, so a converged solve drains the rest of its chunk as empty
+    // launches; the next chunk is already queued while the host waits, so the device
+    // never idles on the host.
+    cudaEvent_t ev[2];
+    IFL_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    IFL_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int rc = IFL_OK;
+    SolveScalars last;
+    auto readback = [&](int sl) -> int {
+        if (cudaMemcpyAsync(&c->scal_h[sl], c->scal, sizeof(SolveScalars), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaEventRecord(ev[sl], st) != cudaSuccess) {
+            set_error("pcg_project: readback enqueue failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return IFL_E_CUDA;
+        }
+        return IFL_OK;
+    };
+    auto wait = [&](int sl) -> int {
+        if (cudaEventSynchronize(ev[sl]) != cudaSuccess) {
+            set_error("pcg_project: %s", cudaGetErrorString(cudaGetLastError()));
+            return IFL_E_CUDA;
+        }
+        last = c->scal_h[sl];
+        if (last.watchdog) {
+            set_error("pcg_project: wavefront dependency watchdog fired");
+            return IFL_E_WATCHDOG;
+        }
+        return IFL_OK;
+    };
+    rc = readback(0); // prologue result (initial |r|inf test)
+    if (rc == IFL_OK) rc = wait(0);
+    const int chunk = 16;
+    int enq = 0, pending = 0, head = 0;
+    while (rc == IFL_OK && !last.done) {
+        while (rc == IFL_OK && pending < 2 && enq < limit) {
+            const int n = imin(chunk, limit - enq);
+            for (int i = 0; i < n && rc == IFL_OK; i++) rc = enqueue_iteration(c);
+            enq += n;
+            if (rc == IFL_OK) rc = readback((head + pending) & 1);
+            pending++;
+        }
+        if (rc != IFL_OK || pending == 0) break;
+        rc = wait(head);
+        head ^= 1;
+        pending--;
+    }
+    if (pending > 0 && cudaStreamSynchronize(st) != cudaSuccess && rc == IFL_OK) { // drain gated no-op launches
+        set_error("pcg_project: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = IFL_E_CUDA;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc != IFL_OK) return rc;
+    if (info) {
+        info->max_error = last.max_error;
+        if (last.done == 2) {
+            info->status = IFL_SOLVE_INITIAL_SMALL;
+            info->iterations = 0;
+        } else if (last.done == 1) {
+            info->status = IFL_SOLVE_CONVERGED;
+            info->iterations = last.iter;
+        } else {
+            info->status = IFL_SOLVE_EXCEEDED;
+            info->iterations = limit;
+        }
+    }
+    return IFL_OK;
+}
+
+} // namespace ifl
