@@ -123,6 +123,11 @@ int ifl_profile(ifl_ctx *ctx, int on);
  * per class (arrays of IFL_K_COUNT_ entries). */
 int ifl_profile_read(ifl_ctx *ctx, double *ms, long long *launches);
 
+/* Diagnostics for the wavefront kernels: arm != 0 makes every following sweep record the
+ * %globaltimer (ns) at which each 32-row strip started and finished; arm == 0 disarms,
+ * copies the last sweep's [strips][2] table into out_ns and returns the strip count. */
+int ifl_debug_sweep_times(ifl_ctx *ctx, int arm, unsigned long long *out_ns, int capacity);
+
 /* ---- data movement (backs FluidQuantity::at()/src(), toImage, test harness) ---- */
 size_t ifl_buf_elems(const ifl_ctx *ctx, int buf);
 int ifl_upload(ifl_ctx *ctx, int buf, const double *host);   /* dense host -> device   */

@@ -39,7 +39,7 @@ KERNEL_CLASSES = ["matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "s
 
 EXPORTS = [
     "ifl_create", "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
-    "ifl_profile", "ifl_profile_read",
+    "ifl_profile", "ifl_profile_read", "ifl_debug_sweep_times",
     "ifl_buf_elems", "ifl_upload", "ifl_download", "ifl_fill",
     "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
@@ -82,6 +82,7 @@ def load_library():
     L.ifl_sync.argtypes = [vp]
     L.ifl_profile.argtypes = [vp, ci]
     L.ifl_profile_read.argtypes = [vp, vp, vp]
+    L.ifl_debug_sweep_times.argtypes = [vp, ci, vp, ci]
     L.ifl_buf_elems.restype = ctypes.c_size_t
     L.ifl_buf_elems.argtypes = [vp, ci]
     L.ifl_upload.argtypes = [vp, ci, vp]
@@ -176,6 +177,16 @@ class FluidSolver:
         n = np.zeros(len(KERNEL_CLASSES), dtype=np.int64)
         self._chk(self.L.ifl_profile_read(self.ctx, ms.ctypes.data, n.ctypes.data))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def sweep_times(self, fn):
+        """Runs fn() with strip timing armed; returns ns[strips, 2] of the LAST sweep fn launched."""
+        self._chk(self.L.ifl_debug_sweep_times(self.ctx, 1, None, 0))
+        fn()
+        buf = np.zeros(2 * ((self.h + 31) // 32), dtype=np.uint64)
+        n = self.L.ifl_debug_sweep_times(self.ctx, 0, buf.ctypes.data, buf.size)
+        if n < 0:
+            self._chk(n)
+        return buf.reshape(-1, 2)
 
     # ---- private hot-path methods of the reference class
     def buildRhs(self):

@@ -233,6 +233,23 @@ int ifl_profile_read(ifl_ctx *c, double *ms, long long *launches) {
     return IFL_OK;
 }
 
+int ifl_debug_sweep_times(ifl_ctx *c, int arm, unsigned long long *out_ns, int capacity) {
+    CHECK_CTX(c);
+    if (arm) {
+        c->sweep_times = c->sweep_times_buf;
+        return IFL_OK;
+    }
+    c->sweep_times = nullptr;
+    if (!out_ns || capacity < 2 * c->n_strips) {
+        set_error("ifl_debug_sweep_times: need room for %d values", 2 * c->n_strips);
+        return IFL_E_ARG;
+    }
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    IFL_CUDA(cudaMemcpy(out_ns, c->sweep_times_buf, (size_t)2 * c->n_strips * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost));
+    return c->n_strips;
+}
+
 long long ifl_launch_count(const ifl_ctx *c) { return c ? c->launches : 0; }
 void *ifl_stream(const ifl_ctx *c) { return c ? (void *)c->stream : nullptr; }
 

@@ -70,6 +70,9 @@ struct ifl_ctx {
     unsigned long long epoch;    // last used handoff epoch
     int n_strips;
     unsigned long long sweep_launches; // sweeps launched so far (ticket base = launches * strips)
+    void *map_cache;                   // TMA tensor maps keyed by array base pointer
+    unsigned long long *sweep_times_buf; // [strips][2] diagnostics buffer
+    unsigned long long *sweep_times;     // == sweep_times_buf while ifl_debug_sweep_times is armed, else null
     long long launches;
     // per-kernel-class event timing (ifl_profile): ring of (start, stop, class)
     int prof_on;

@@ -24,11 +24,12 @@
 //         behind lane t-1, i.e. the warp is one anti-diagonal.  The left neighbour is
 //         the lane's own previous value (register), the upper neighbour arrives by
 //         __shfl_up.  Operands are read from shared-memory tiles at skewed addresses
-//         (row pitch 34 doubles -> conflict-free), one step ahead of their use, so the
+//         (dense 32-double rows: the skew itself staggers the banks), one step ahead of their use, so the
 //         per-step cost is the 4-deep dependent FP64 chain and nothing else.
-//       warp 1 (loader): streams the strip's operand tiles HBM -> smem with
-//         cp.async.bulk (TMA, one 256-byte row per copy) into an N-stage ring, and
-//         polls the upstream strip's last row out of the hand-off buffer.
+//       warp 1 (loader): streams the strip's operand tiles HBM -> smem with 2-D
+//         tensor-map TMA (cp.async.bulk.tensor, one 33x32 box per operand per block)
+//         into an N-stage ring, N-2 blocks ahead of the compute warp, and polls the
+//         upstream strip's last row out of the hand-off buffer.
 //       warp 2 (storer): drains finished result tiles smem -> HBM with 16-byte stores.
 //     Stages are recycled through mbarriers (full / done / empty).
 //   * Strip-to-strip hand-off of the swept variable uses NCCL-LL style 16-byte
@@ -41,43 +42,49 @@
 //     boundary predicates at all.  Pad results are never stored.
 #include "ifl_internal.cuh"
 
+#include <cuda.h>
 #include <string.h>
 
 namespace ifl {
 
 enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3 };
 
-constexpr int TP = 34;                          // tile row pitch in doubles (272 B: 16B aligned, conflict-free skew)
-constexpr int TROWS = 33;                       // row 0 = upstream halo row, rows 1..32 = the strip
-constexpr int TILE_DOUBLES = TROWS * TP;        // 1122
-constexpr int TILE_BYTES = TILE_DOUBLES * 8;    // 8976 (multiple of 16)
+// A tile is one TMA box: 33 rows x 32 doubles, dense (256-byte rows).  Forward kinds
+// fetch memory rows y0-1 .. y0+31 (tile row 0 = the upstream strip's last row, lane t
+// owns tile row 1+t); the backward kind fetches y0 .. y0+32 (lane t owns tile row 31-t,
+// tile row 32 = upstream).  Either way the upstream-row operand of a lane sits one tile
+// row "before" its own row in sweep order: UP_OFF doubles away.
+constexpr int TP = 32;
+constexpr int TROWS = 33;
+constexpr int TILE_DOUBLES = TROWS * TP;     // 1056
+constexpr int TILE_BYTES = TILE_DOUBLES * 8; // 8448 (multiple of 128)
 constexpr int MAX_TILES = 6;
-constexpr unsigned WATCHDOG_POLLS = 1u << 24;
+constexpr int MAX_STAGES = 8;
+constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
+constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
 
 struct TileDesc {
-    double *p; // array base (pitched)
-    int load;  // fetched HBM -> smem
-    int row_shift; // fetch memory row (strip row + row_shift) instead of the strip row itself
-    int halo;  // row 0 fetched from the upstream memory row as well
-    int store; // drained smem -> HBM
+    double *p;     // array base (pitched) -- used by the storer
+    int load;      // fetched HBM -> smem by TMA
+    int row_shift; // fetch memory rows shifted by this many rows (Gauss-Seidel: the row below)
+    int store;     // drained smem -> HBM
 };
 
 struct SweepParams {
+    CUtensorMap map[MAX_TILES]; // one per loaded tile (must stay first: 64-byte aligned)
     TileDesc t[MAX_TILES];
-    int nt;       // tiles per stage
-    int nst;      // ring depth
-    int swept;    // tile index of the swept variable (halo row comes from the hand-off buffer)
+    int nt;    // tiles per stage
+    int nst;   // ring depth
     int W, H, pitch, nbx, nby;
-    int backward;
     uint4 *handoff; // [nby][nbx*32]
     unsigned epoch;
     unsigned long long *ticket;
     unsigned long long ticket_base;
     SolveScalars *scal;
-    int gated;         // skip when scal->done
-    double *partials;  // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
-    int with_dot;
-    double scale;      // KIND_GS: timestep/(density*hx*hx)  v2:234
+    int gated;        // skip when scal->done
+    double *partials; // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
+    double scale;     // KIND_GS: timestep/(density*hx*hx)  v2:234
+    unsigned long long *times; // diagnostics: [nby][2] globaltimer ns at strip start / end (or null)
 };
 
 // ------------------------------------------------------------------ PTX helpers ----
@@ -91,47 +98,81 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+// Bounded wait: every dependency wait in this file gives up after a (very long) poll
+// budget, raises the watchdog flags and lets the kernel run to completion with garbage,
+// so that a protocol bug can never hang the device.  `dead` is a CTA-wide shared flag.
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
 }
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity, volatile int *dead, SolveScalars *scal) {
+    if (mbar_try(bar, parity)) return;
+    if (*dead) return;
+    unsigned n = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++n > WATCHDOG_TRIES || *dead) {
+            *dead = 1;
+            scal->watchdog = 1;
+            return;
+        }
+    }
+}
+// TMA: one 2-D box global -> shared, completion counted in bytes on an mbarrier.
+// Out-of-range rows (y = -1 for the first strip) are filled with zeros by the hardware.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch) {
+// NCCL-LL style message: {lo, epoch, hi, epoch} in one 16-byte store / load.
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch, bool pred) {
+    // predicated inside the asm so that the per-step publish needs no branch
     const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
-                 : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %5, 0;\n\t"
+        "@p st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t"
+        "}" ::"l"(dst),
+        "r"(lo), "r"(epoch), "r"(hi), "r"(epoch), "r"((unsigned)pred)
+        : "memory");
 }
 __device__ __forceinline__ bool ll_load(const uint4 *src, unsigned epoch, double &v) {
     unsigned a, b, c, d;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
     v = __hiloint2double((int)c, (int)a);
     return b == epoch && d == epoch;
 }
 
 // ---------------------------------------------------------------- compute warp ----
+template <int KIND>
+struct Geo {
+    static constexpr bool BWD = (KIND == KIND_BWD);
+    static constexpr int UP_OFF = BWD ? TP : -TP; // own row -> upstream row, in doubles
+    __device__ static __forceinline__ int lane_row(int lane) { return BWD ? 31 - lane : 1 + lane; }
+    // tile column of logical in-block column ci (backward sweeps walk the tile right to left)
+    __device__ static __forceinline__ int tcol(int ci) { return BWD ? 31 - ci : ci; }
+};
+
 // Per-lane state carried from column to column.
 struct Carry {
     double zprev; // swept variable of the previous column (own row)
-    double c1;    // FWD: cx of previous column | FACTOR: cx of previous column
-    double c2;    // FACTOR: cy of previous column
+    double c1;    // FWD / FACTOR: cx of the previous column
+    double c2;    // FACTOR: cy of the previous column
     double acc;   // BWD: running z.r | GS: running max |p - newP|
 };
 
@@ -140,37 +181,36 @@ struct Ops {
     double a, b, c, d, e, halo;
 };
 
+// p -> tile 0, this lane's row, this step's column; tile k sits k*TILE_DOUBLES further.
+// p_right (KIND_GS only) -> tile 0, same row, next logical column (may be in the next block).
+// ph (lane 0 only) -> the swept variable of the upstream strip's last row at this column.
 template <int KIND, bool DOT>
-__device__ __forceinline__ void fetch(Ops &o, const double *p, const double *p_right, int lane) {
-    // p -> tile 0, this lane's row, this step's column.  Tile k sits k*TILE_DOUBLES further.
-    // p_right (KIND_GS only) -> tile 0, same row, next logical column (may sit in the next block).
+__device__ __forceinline__ void fetch(Ops &o, const double *p, const double *p_right, const double *ph, int lane) {
+    constexpr int UP = Geo<KIND>::UP_OFF;
     if (KIND == KIND_GS) {
-        o.a = p[0];                      // p (old)            own cell, updated in place
-        o.b = p_right[0];                // p (old)            right cell
-        o.c = p[1 * TILE_DOUBLES];       // p (old)            lower cell (tile 1 = p fetched one row down)
-        o.d = p[2 * TILE_DOUBLES];       // r                  own cell
-        if (lane == 0) o.halo = p[-TP];  // p (new) of the upstream strip's last row
+        o.a = p[0];                // p (old)  own cell, updated in place
+        o.b = p_right[0];          // p (old)  right cell
+        o.c = p[1 * TILE_DOUBLES]; // p (old)  lower cell (tile 1 = p fetched one row down)
+        o.d = p[2 * TILE_DOUBLES]; // r        own cell
     } else if (KIND == KIND_FWD) {
-        o.a = p[0];                      // a (rhs)            own cell
-        o.b = p[1 * TILE_DOUBLES];       // cx                 own cell (carried to the next step)
-        o.c = p[2 * TILE_DOUBLES - TP];  // cy                 upper cell (tile row 0 = halo row)
-        o.d = p[3 * TILE_DOUBLES];       // precon             own cell
-        if (lane == 0) o.halo = p[4 * TILE_DOUBLES - TP]; // z of the upstream strip's last row
+        o.a = p[0];                     // a (rhs)  own cell
+        o.b = p[1 * TILE_DOUBLES];      // cx       own cell (carried to the next step)
+        o.c = p[2 * TILE_DOUBLES + UP]; // cy       upper cell
+        o.d = p[3 * TILE_DOUBLES];      // precon   own cell
     } else if (KIND == KIND_BWD) {
-        o.a = p[0];                      // z (forward result) own cell, updated in place
-        o.b = p[1 * TILE_DOUBLES];       // cx own
-        o.c = p[2 * TILE_DOUBLES];       // cy own
-        o.d = p[3 * TILE_DOUBLES];       // precon own
+        o.a = p[0];                         // z (forward result) own cell, updated in place
+        o.b = p[1 * TILE_DOUBLES];          // cx own
+        o.c = p[2 * TILE_DOUBLES];          // cy own
+        o.d = p[3 * TILE_DOUBLES];          // precon own
         if (DOT) o.e = p[4 * TILE_DOUBLES]; // r own
-        if (lane == 0) o.halo = p[-TP];
     } else {
-        o.a = p[0];                      // aDiag own
-        o.b = p[1 * TILE_DOUBLES];       // aPlusX own
-        o.c = p[2 * TILE_DOUBLES];       // aPlusY own
-        o.d = p[1 * TILE_DOUBLES - TP];  // aPlusX upper
-        o.e = p[2 * TILE_DOUBLES - TP];  // aPlusY upper
-        if (lane == 0) o.halo = p[3 * TILE_DOUBLES - TP]; // precon of the upstream strip's last row
+        o.a = p[0];                     // aDiag own
+        o.b = p[1 * TILE_DOUBLES];      // aPlusX own
+        o.c = p[2 * TILE_DOUBLES];      // aPlusY own
+        o.d = p[1 * TILE_DOUBLES + UP]; // aPlusX upper
+        o.e = p[2 * TILE_DOUBLES + UP]; // aPlusY upper
     }
+    if (lane == 0) o.halo = ph[0];
 }
 
 // Per-lane constants of a Gauss-Seidel sweep.
@@ -232,64 +272,76 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, doubl
     return znew;
 }
 
-// tile column of logical in-block column ci (backward sweeps walk the tile right to left)
-template <int KIND>
-__device__ __forceinline__ int tcol(int ci) {
-    return (KIND == KIND_BWD) ? 31 - ci : ci;
-}
+// Per-lane tile-0 base pointers of one macro-step.  Logical position j (= kk + look-ahead,
+// 0..33) of this lane lies in block m-1 when j < lane, in block m when j - lane < 32 and
+// in block m+1 otherwise (lanes 0/1 only); each base already contains the lane's row and
+// its skew, so the address is always `base + DIR*j` and j folds into the instruction's
+// immediate offset.  Positions that do not exist (first / last macro-step) alias valid
+// memory and are never used.
+struct LaneBases {
+    double *A; // block m
+    double *B; // block m-1
+    double *N; // block m+1
+};
 
-// Tile-0 address of the in-macro-step column offset d (logical column 32m + d) in this
-// lane's row.  d < 0 lies in block m-1, 0..31 in block m, >= 32 in block m+1.  EDGE 1:
-// block m-1 does not exist (first macro-step), EDGE 2: block m does not exist (last
-// macro-step); such positions are clamped to valid memory and their values never used.
-template <int KIND, int EDGE>
-__device__ __forceinline__ double *ptr_of(int d, double *s_prev, double *s_cur, double *s_next) {
-    if (EDGE == 1) return (d < 0) ? s_cur + tcol<KIND>(0) : (d < 32 ? s_cur + tcol<KIND>(d) : s_next + tcol<KIND>(d - 32));
-    if (EDGE == 2) return (d < 0) ? s_prev + tcol<KIND>(32 + d) : s_prev + tcol<KIND>(31);
-    return (d < 0) ? s_prev + tcol<KIND>(32 + d) : (d < 32 ? s_cur + tcol<KIND>(d) : s_next + tcol<KIND>(d - 32));
+template <int KIND>
+__device__ __forceinline__ double *pos(const LaneBases &lb, int j, int lane) {
+    constexpr int DIR = Geo<KIND>::BWD ? -1 : 1;
+    double *base = (lane > j) ? lb.B : lb.A;
+    if (j >= 32) base = (lane <= j - 32) ? lb.N : base; // j is a compile-time constant
+    return base + DIR * j;
 }
 
 // One macro-step = 32 steps of the skewed warp.  During macro-step m lane t works on
-// logical columns 32m-t .. 32m-t+31, i.e. the tail of block m-1 (`s_prev`) and the
-// head of block m (`s_cur`); the operands of each step are fetched one step early,
-// which can reach into block m+1 (`s_next`, lane 0 only).  All three pointers already
-// include this lane's tile-row offset.  EDGE: 0 interior, 1 first macro-step (lanes
-// that have not entered the strip idle), 2 last macro-step (lanes that have left idle).
+// logical columns 32m-t .. 32m-t+31, i.e. the tail of block m-1 and the head of block m.
+// Per step the only serial dependency is  z -> shuffle -> 3 FP64 ops -> z ; the shuffle
+// is issued first and the operand fetch for the NEXT step (shared-memory loads at
+// branch-free addresses) runs in its shadow.  EDGE: 0 interior, 1 first macro-step
+// (lanes that have not entered the strip idle), 2 last macro-step (lanes that have left
+// the strip idle).
 template <int KIND, bool DOT, int EDGE>
-__device__ __forceinline__ void macro_step(double *s_prev, double *s_cur, double *s_next, uint64_t *full_next,
-                                           unsigned parity_next, bool wait_next, int m, int lane, Carry &cr,
-                                           Ops &ops, uint4 *handoff_row, bool publish, unsigned epoch,
-                                           const GsConst &gs) {
+__device__ __forceinline__ void macro_step(const LaneBases &lb, const double *h_cur, const double *h_next,
+                                           uint64_t *full_next, unsigned parity_next, bool wait_next, int m, int lane,
+                                           Carry &cr, Ops &ops, uint4 *handoff_row, bool publish, unsigned epoch,
+                                           const GsConst &gs, volatile int *dead, SolveScalars *scal) {
+    typedef Geo<KIND> G;
+    constexpr int DIR = G::BWD ? -1 : 1;
     // Gauss-Seidel also reads the right neighbour, i.e. looks one column further ahead
     constexpr int WAIT_KK = (KIND == KIND_GS) ? 30 : 31;
 #pragma unroll
     for (int kk = 0; kk < 32; kk++) {
-        // ---- operands of step kk+1, issued before this step's stores
-        Ops nxt = ops;
-        if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next); // lane 0 is about to touch block m+1
+        if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next, dead, scal); // lane 0 is about to touch block m+1
+        // ---- critical path first: the upper neighbour's value of the previous step
+        double up = __shfl_up_sync(0xffffffffu, cr.zprev, 1);
+        // ---- operands of step kk+1, in the shadow of the shuffle
+        Ops nxt;
         {
-            const int d = kk + 1 - lane;
-            const double *pn = ptr_of<KIND, EDGE>(d, s_prev, s_cur, s_next);
-            const double *pr = (KIND == KIND_GS) ? ptr_of<KIND, EDGE>(d + 1, s_prev, s_cur, s_next) : pn;
-            fetch<KIND, DOT>(nxt, pn, pr, lane);
-            if (KIND == KIND_GS && !(32 * m + d + 1 < gs.W)) nxt.b = 0.0; // no right neighbour (v2:258)
+            const double *pn = pos<KIND>(lb, kk + 1, lane);
+            const double *pr = (KIND == KIND_GS) ? pos<KIND>(lb, kk + 2, lane) : pn;
+            const double *ph = (kk + 1 < 32) ? h_cur + DIR * (kk + 1) : h_next + DIR * (kk + 1 - 32);
+            nxt.halo = ops.halo;
+            fetch<KIND, DOT>(nxt, pn, pr, ph, lane);
+            if (KIND == KIND_GS && !(32 * m + kk + 2 - lane < gs.W)) nxt.b = 0.0; // no right neighbour (v2:258)
         }
         // ---- this step
         const int d0 = kk - lane;
         const bool active = (EDGE == 0) ? true : (EDGE == 1 ? d0 >= 0 : d0 < 0);
-        double *p = ptr_of<KIND, EDGE>(d0, s_prev, s_cur, s_next);
-        double up = __shfl_up_sync(0xffffffffu, cr.zprev, 1);
+        double *p = pos<KIND>(lb, kk, lane);
         if (lane == 0) up = ops.halo;
         if (active) {
             const double z = cell<KIND, DOT>(ops, cr, up, p, 32 * m + d0, gs);
-            if (publish && lane == 31) ll_store(handoff_row + 32 * m + d0, z, epoch);
+            ll_store(handoff_row + 32 * m + d0, z, epoch, publish && lane == 31);
         }
         ops = nxt;
     }
 }
 
 template <int KIND, bool DOT>
-__device__ void compute_warp(const SweepParams &P, double *smem, uint64_t *full, uint64_t *done, int sj, int lane) {
+__device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *full, uint64_t *done, int sj,
+                             int lane, volatile int *dead) {
+    typedef Geo<KIND> G;
+    constexpr int DIR = G::BWD ? -1 : 1;
+    constexpr int COL0 = G::BWD ? 31 : 0; // tile column of logical in-block column 0
     Carry cr;
     cr.zprev = 0.0;
     cr.c1 = 0.0;
@@ -299,7 +351,7 @@ __device__ void compute_warp(const SweepParams &P, double *smem, uint64_t *full,
     uint4 *handoff_row = P.handoff + (size_t)sj * P.nbx * 32;
     const int nst = P.nst, nbx = P.nbx;
     const int stage_doubles = P.nt * TILE_DOUBLES;
-    double *row0 = smem + (1 + lane) * TP; // this lane's row in tile 0 of stage 0
+    double *row0 = smem + G::lane_row(lane) * TP + COL0; // this lane's row in tile 0 of stage 0, logical column 0
     GsConst gs;
     gs.scale = P.scale;
     gs.d1 = 0.0 + P.scale;
@@ -315,25 +367,38 @@ __device__ void compute_warp(const SweepParams &P, double *smem, uint64_t *full,
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
-    mbar_wait(&full[0], 0);
-    fetch<KIND, DOT>(ops, row0 + tcol<KIND>(0), row0 + tcol<KIND>(1), lane);
+    mbar_wait(&full[0], 0, dead, P.scal);
+    fetch<KIND, DOT>(ops, row0, row0 + DIR, halo_s + COL0, lane);
     if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
     unsigned par_next = 0;                        // parity of full[sn] for block m+1
     for (int m = 0; m <= nbx; m++) {
+        const bool has_next = m + 1 < nbx;
         double *s_prev = row0 + sp * stage_doubles;
         double *s_cur = row0 + sc * stage_doubles;
-        const bool has_next = m + 1 < nbx;
-        double *s_next = has_next ? row0 + sn * stage_doubles : s_prev;
-        if (m == 0)
-            macro_step<KIND, DOT, 1>(s_prev, s_cur, s_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs);
-        else if (m == nbx)
-            macro_step<KIND, DOT, 2>(s_prev, s_cur, s_next, &full[sn], par_next, false, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs);
-        else
-            macro_step<KIND, DOT, 0>(s_prev, s_cur, s_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs);
+        double *s_next = row0 + sn * stage_doubles;
+        const double *h_cur = halo_s + sc * 32 + COL0;
+        const double *h_next = halo_s + (has_next ? sn : sc) * 32 + COL0;
+        LaneBases lb;
+        if (m == 0) { // no block m-1: idle lanes alias block 0
+            lb.A = s_cur - DIR * lane;
+            lb.B = lb.A;
+            lb.N = has_next ? s_next - DIR * (32 + lane) : lb.A;
+            macro_step<KIND, DOT, 1>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
+                                     publish, P.epoch, gs, dead, P.scal);
+        } else if (m == nbx) { // no block m: idle lanes alias block m-1
+            lb.B = s_prev + DIR * (32 - lane);
+            lb.A = s_prev - DIR * lane;
+            lb.N = lb.A;
+            macro_step<KIND, DOT, 2>(lb, h_cur, h_next, &full[sn], par_next, false, m, lane, cr, ops, handoff_row,
+                                     publish, P.epoch, gs, dead, P.scal);
+        } else {
+            lb.A = s_cur - DIR * lane;
+            lb.B = s_prev + DIR * (32 - lane);
+            lb.N = has_next ? s_next - DIR * (32 + lane) : lb.A;
+            macro_step<KIND, DOT, 0>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
+                                     publish, P.epoch, gs, dead, P.scal);
+        }
         if (m >= 1) {
             // block m-1 is complete in smem: hand it to the storer (and, through it, the loader)
             fence_proxy_async();
@@ -358,49 +423,56 @@ __device__ void compute_warp(const SweepParams &P, double *smem, uint64_t *full,
 }
 
 // ----------------------------------------------------------------- loader warp ----
-__device__ void loader_warp(const SweepParams &P, double *smem, uint64_t *full, uint64_t *empty, int sj, int lane) {
-    const int nst = P.nst;
+// Keeps the TMA ring `nst-3` blocks ahead of the block whose hand-off row it is
+// currently waiting for.  The compute warp releases block j only at the end of
+// macro-step j+1, and inside that macro-step it already waits for block j+2; block j
+// therefore drains only after the hand-off row of block j+2 has been delivered, and a
+// window deeper than nst-3 would make the loader wait for a stage that cannot drain.
+template <int KIND>
+__device__ void loader_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *full, uint64_t *empty, int sj,
+                            int lane, volatile int *dead) {
+    typedef Geo<KIND> G;
+    const int nst = P.nst, nbx = P.nbx;
     const int stage_doubles = P.nt * TILE_DOUBLES;
-    const bool bwd = P.backward != 0;
-    const int ty = bwd ? (P.nby - 1 - sj) : sj;   // memory tile row of this strip
-    const int y0 = ty * 32;
-    const int my_row = bwd ? (y0 + 31 - lane) : (y0 + lane); // memory row behind tile row 1+lane
-    const int halo_row = bwd ? (y0 + 32) : (y0 - 1);
-    const bool has_up = sj > 0; // an upstream strip exists (halo rows are real data)
-    // bytes that will land per stage
-    unsigned bytes = 0;
-    for (int k = 0; k < P.nt; k++)
-        if (P.t[k].load) bytes += 32u * 256u + ((P.t[k].halo && has_up) ? 256u : 0u);
-    const uint4 *up_row = P.handoff + (size_t)(sj - 1) * P.nbx * 32;
+    const int ty = G::BWD ? (P.nby - 1 - sj) : sj; // memory tile row of this strip
+    const int box_y = G::BWD ? ty * 32 : ty * 32 - 1;
+    const bool has_up = sj > 0;
+    int nload = 0;
+    for (int k = 0; k < P.nt; k++) nload += P.t[k].load ? 1 : 0;
+    const unsigned bytes = (unsigned)nload * TILE_BYTES;
+    const uint4 *up_row = P.handoff + (size_t)(has_up ? sj - 1 : 0) * nbx * 32;
+    const int ahead = nst - 3;
     unsigned polls = 0;
+    int issued = 0;
 
-    for (int m = 0; m < P.nbx; m++) {
-        const int st = m % nst;
-        double *stage = smem + st * stage_doubles;
-        if (m >= nst) mbar_wait(&empty[st], ((m / nst) - 1) & 1);
-        const int tx = bwd ? (P.nbx - 1 - m) : m; // memory tile column
-        const size_t col0 = (size_t)tx * 32;
-        if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
-        __syncwarp();
-        for (int k = 0; k < P.nt; k++) {
-            if (!P.t[k].load) continue;
-            double *tile = stage + k * TILE_DOUBLES;
-            bulk_g2s(tile + (1 + lane) * TP, P.t[k].p + col0 + (size_t)(my_row + P.t[k].row_shift) * P.pitch, 256,
-                     &full[st]);
-            if (P.t[k].halo && has_up && lane == 0)
-                bulk_g2s(tile, P.t[k].p + col0 + (size_t)halo_row * P.pitch, 256, &full[st]);
+    for (int m = 0; m < nbx; m++) {
+        while (issued < nbx && issued <= m + ahead) {
+            const int st = issued % nst;
+            if (issued >= nst) mbar_wait(&empty[st], ((issued / nst) - 1) & 1, dead, P.scal);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[st], bytes);
+                const int box_x = (G::BWD ? (nbx - 1 - issued) : issued) * 32;
+                double *stage = smem + st * stage_doubles;
+                for (int k = 0; k < P.nt; k++)
+                    if (P.t[k].load)
+                        tma_load_2d(stage + k * TILE_DOUBLES, &P.map[k], box_x, box_y + P.t[k].row_shift, &full[st]);
+            }
+            __syncwarp();
+            issued++;
         }
-        // swept variable of the upstream strip's last row -> tile row 0 (LL hand-off)
+        // swept variable of the upstream strip's last row (LL hand-off) -> halo_s[stage]
+        const int st = m % nst;
         if (has_up) {
             double v = 0.0;
             const uint4 *src = up_row + (size_t)m * 32 + lane;
             while (!ll_load(src, P.epoch, v)) {
-                if (++polls > WATCHDOG_POLLS) {
+                if (++polls > WATCHDOG_POLLS || *dead) {
+                    *dead = 1;
                     P.scal->watchdog = 1;
                     break;
                 }
             }
-            stage[P.swept * TILE_DOUBLES + (bwd ? 31 - lane : lane)] = v;
+            halo_s[st * 32 + G::tcol(lane)] = v;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
@@ -408,18 +480,20 @@ __device__ void loader_warp(const SweepParams &P, double *smem, uint64_t *full, 
 }
 
 // ----------------------------------------------------------------- storer warp ----
-__device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, uint64_t *empty, int sj, int lane) {
+template <int KIND>
+__device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, uint64_t *empty, int sj, int lane,
+                            volatile int *dead) {
+    typedef Geo<KIND> G;
     const int nst = P.nst;
     const int stage_doubles = P.nt * TILE_DOUBLES;
-    const bool bwd = P.backward != 0;
-    const int ty = bwd ? (P.nby - 1 - sj) : sj;
+    const int ty = G::BWD ? (P.nby - 1 - sj) : sj;
     const int y0 = ty * 32;
     const int half = lane >> 4, l16 = lane & 15;
     for (int m = 0; m < P.nbx; m++) {
         const int st = m % nst;
         double *stage = smem + st * stage_doubles;
-        mbar_wait(&done[st], (m / nst) & 1);
-        const int tx = bwd ? (P.nbx - 1 - m) : m;
+        mbar_wait(&done[st], (m / nst) & 1, dead, P.scal);
+        const int tx = G::BWD ? (P.nbx - 1 - m) : m;
         const int x = tx * 32 + l16 * 2;
         for (int k = 0; k < P.nt; k++) {
             if (!P.t[k].store) continue;
@@ -427,9 +501,10 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
             double *g = P.t[k].p;
 #pragma unroll 4
             for (int i = 0; i < 16; i++) {
-                const int lr = i * 2 + half; // lane-row inside the strip (tile row 1+lr)
-                const int y = bwd ? (y0 + 31 - lr) : (y0 + lr);
-                const double2 v = *reinterpret_cast<const double2 *>(tile + (1 + lr) * TP + l16 * 2);
+                const int ry = i * 2 + half; // row inside the strip, memory order
+                const int trow = G::BWD ? ry : 1 + ry;
+                const int y = y0 + ry;
+                const double2 v = *reinterpret_cast<const double2 *>(tile + trow * TP + l16 * 2);
                 if (y < P.H) {
                     double *dst = g + x + (size_t)y * P.pitch;
                     if (x + 1 < P.W)
@@ -447,18 +522,21 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
 
 // ---------------------------------------------------------------------- kernel ----
 template <int KIND, bool DOT>
-__global__ void __launch_bounds__(96, 1) k_sweep(const SweepParams P) {
+__global__ void __launch_bounds__(96, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bars[3 * 8]; // full[nst], done[nst], empty[nst] (nst <= 8)
+    __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
     __shared__ int s_strip;
+    __shared__ int s_dead;
     double *smem = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = bars, *done = bars + 8, *empty = bars + 16;
+    double *halo_s = smem + P.nst * P.nt * TILE_DOUBLES; // [nst][32] hand-off rows
+    uint64_t *full = bars, *done = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         // ticket first (keeps the global count consistent even for gated launches)
         const unsigned long long tk = atomicAdd(P.ticket, 1ULL);
         s_strip = (int)(tk - P.ticket_base);
+        s_dead = 0;
         for (int i = 0; i < P.nst; i++) {
             mbar_init(&full[i], 2);  // loader: expect_tx arrive + hand-off arrive
             mbar_init(&done[i], 1);  // compute warp
@@ -466,27 +544,89 @@ __global__ void __launch_bounds__(96, 1) k_sweep(const SweepParams P) {
         }
         fence_mbar_init();
     }
+    // the first strip has no upstream row: its hand-off rows read +0.0
+    for (int i = threadIdx.x; i < P.nst * 32; i += blockDim.x) halo_s[i] = 0.0;
     __syncthreads();
     if (P.gated && P.scal->done) return;
     const int sj = s_strip;
 
-    // tile row 0 of every tile starts as +0.0: the first strip has no upstream row
-    for (int i = threadIdx.x; i < P.nst * P.nt * TP; i += blockDim.x) {
-        const int tile = i / TP, col = i % TP;
-        smem[tile * TILE_DOUBLES + col] = 0.0;
+    if (warp == 0) {
+        unsigned long long t0 = 0;
+        if (P.times && lane == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        compute_warp<KIND, DOT>(P, smem, halo_s, full, done, sj, lane, &s_dead);
+        if (P.times && lane == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            P.times[2 * sj] = t0;
+            P.times[2 * sj + 1] = t1;
+        }
     }
-    fence_proxy_async();
-    __syncthreads();
-
-    if (warp == 0)
-        compute_warp<KIND, DOT>(P, smem, full, done, sj, lane);
     else if (warp == 1)
-        loader_warp(P, smem, full, empty, sj, lane);
+        loader_warp<KIND>(P, smem, halo_s, full, empty, sj, lane, &s_dead);
     else
-        storer_warp(P, smem, done, empty, sj, lane);
+        storer_warp<KIND>(P, smem, done, empty, sj, lane, &s_dead);
 }
 
 // ------------------------------------------------------------------- host side ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// Tensor map of one pitched cell array: 2-D, double, box = 32 columns x 33 rows, no
+// swizzle (the skewed access pattern is conflict-free on dense rows), zero OOB fill.
+// Maps are cached per base pointer (flip() only swaps pointers).
+struct MapCache {
+    enum { N = 32 };
+    void *key[N];
+    CUtensorMap map[N];
+    int n;
+};
+
+static int get_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
+    MapCache *mc = (MapCache *)c->map_cache;
+    for (int i = 0; i < mc->n; i++)
+        if (mc->key[i] == a.p) {
+            *out = mc->map[i];
+            return IFL_OK;
+        }
+    PFN_encodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return IFL_E_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.pitch, (cuuint64_t)a.rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.pitch * sizeof(double)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.p, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d array", (int)r, a.w, a.h);
+        return IFL_E_CUDA;
+    }
+    if (mc->n < MapCache::N) {
+        mc->key[mc->n] = a.p;
+        mc->map[mc->n] = m;
+        mc->n++;
+    }
+    *out = m;
+    return IFL_OK;
+}
+
 int sweep_init(ifl_ctx *c) {
     const int nbx = (c->W + 31) / 32, nby = (c->H + 31) / 32;
     c->n_strips = nby;
@@ -494,6 +634,9 @@ int sweep_init(ifl_ctx *c) {
     IFL_CUDA(cudaMemset(c->handoff, 0, (size_t)nby * nbx * 32 * sizeof(uint4)));
     IFL_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned long long)));
     IFL_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned long long)));
+    IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 2 * sizeof(unsigned long long)));
+    c->map_cache = calloc(1, sizeof(MapCache));
+    if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
     return IFL_OK;
 }
@@ -501,12 +644,32 @@ int sweep_init(ifl_ctx *c) {
 void sweep_free(ifl_ctx *c) {
     if (c->handoff) cudaFree(c->handoff);
     if (c->ticket) cudaFree(c->ticket);
+    if (c->sweep_times_buf) cudaFree(c->sweep_times_buf);
+    free(c->map_cache);
     c->handoff = nullptr;
     c->ticket = nullptr;
+    c->map_cache = nullptr;
 }
 
+struct TileSpec {
+    const Arr *a;
+    int load, row_shift, store;
+};
+
 template <int KIND, bool DOT>
-static int launch_sweep(ifl_ctx *c, SweepParams &P) {
+static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt, int nst) {
+    P.nt = nt;
+    P.nst = nst;
+    for (int k = 0; k < nt; k++) {
+        P.t[k].p = spec[k].a->p;
+        P.t[k].load = spec[k].load;
+        P.t[k].row_shift = spec[k].row_shift;
+        P.t[k].store = spec[k].store;
+        if (spec[k].load) {
+            int rc = get_map(c, *spec[k].a, &P.map[k]);
+            if (rc != IFL_OK) return rc;
+        }
+    }
     P.W = c->W;
     P.H = c->H;
     P.pitch = c->r.pitch;
@@ -519,11 +682,12 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P) {
         c->epoch++;
         P.epoch = 1;
     }
-    P.ticket = reinterpret_cast<unsigned long long *>(c->ticket);
+    P.ticket = c->ticket;
     P.ticket_base = c->sweep_launches * (unsigned long long)P.nby;
     c->sweep_launches++;
     P.scal = c->scal;
-    const size_t smem = (size_t)P.nst * P.nt * TILE_BYTES;
+    P.times = c->sweep_times;
+    const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)nst * 32 * sizeof(double);
     static bool attr_set[4][2] = {{false, false}, {false, false}, {false, false}, {false, false}};
     if (!attr_set[KIND][DOT]) {
         IFL_CUDA(cudaFuncSetAttribute(k_sweep<KIND, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
@@ -535,67 +699,33 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P) {
     return IFL_OK;
 }
 
-static TileDesc tile(const Arr &a, int load, int halo, int store) {
-    TileDesc t;
-    t.p = a.p;
-    t.load = load;
-    t.row_shift = 0;
-    t.halo = halo;
-    t.store = store;
-    return t;
-}
-
 int launch_mic0_factor(ifl_ctx *c) {
     SweepParams P;
     memset(&P, 0, sizeof P);
-    P.nt = 6;
-    P.nst = 4;
-    P.swept = 3;
-    P.t[0] = tile(c->aDiag, 1, 0, 0);
-    P.t[1] = tile(c->aPlusX, 1, 1, 0);
-    P.t[2] = tile(c->aPlusY, 1, 1, 0);
-    P.t[3] = tile(c->precon, 0, 0, 1);
-    P.t[4] = tile(c->cx, 0, 0, 1);
-    P.t[5] = tile(c->cy, 0, 0, 1);
-    return launch_sweep<KIND_FACTOR, false>(c, P);
+    const TileSpec spec[6] = {{&c->aDiag, 1, 0, 0}, {&c->aPlusX, 1, 0, 0}, {&c->aPlusY, 1, 0, 0},
+                              {&c->precon, 0, 0, 1}, {&c->cx, 0, 0, 1},    {&c->cy, 0, 0, 1}};
+    return launch_sweep<KIND_FACTOR, false>(c, P, spec, 6, 4);
 }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
     SweepParams P;
     memset(&P, 0, sizeof P);
-    P.nt = 5;
-    P.nst = 5;
-    P.swept = 4;
     P.gated = gated ? 1 : 0;
-    P.t[0] = tile(a, 1, 0, 0);
-    P.t[1] = tile(c->cx, 1, 0, 0);
-    P.t[2] = tile(c->cy, 1, 1, 0);
-    P.t[3] = tile(c->precon, 1, 0, 0);
-    P.t[4] = tile(dst, 0, 0, 1);
-    return launch_sweep<KIND_FWD, false>(c, P);
+    const TileSpec spec[5] = {{&a, 1, 0, 0}, {&c->cx, 1, 0, 0}, {&c->cy, 1, 0, 0}, {&c->precon, 1, 0, 0}, {&dst, 0, 0, 1}};
+    return launch_sweep<KIND_FWD, false>(c, P, spec, 5, 5);
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
     SweepParams P;
     memset(&P, 0, sizeof P);
-    P.backward = 1;
-    P.nst = 5;
-    P.swept = 0;
     P.gated = gated ? 1 : 0;
-    P.t[0] = tile(dst, 1, 0, 1);
-    P.t[1] = tile(c->cx, 1, 0, 0);
-    P.t[2] = tile(c->cy, 1, 0, 0);
-    P.t[3] = tile(c->precon, 1, 0, 0);
+    const TileSpec spec[5] = {{&dst, 1, 0, 1}, {&c->cx, 1, 0, 0}, {&c->cy, 1, 0, 0}, {&c->precon, 1, 0, 0}, {&r_for_dot, 1, 0, 0}};
     if (with_dot) {
-        P.nt = 5;
-        P.t[4] = tile(r_for_dot, 1, 0, 0);
-        P.with_dot = 1;
         P.partials = c->partials;
         c->n_partials = (c->H + 31) / 32;
-        return launch_sweep<KIND_BWD, true>(c, P);
+        return launch_sweep<KIND_BWD, true>(c, P, spec, 5, 5);
     }
-    P.nt = 4;
-    return launch_sweep<KIND_BWD, false>(c, P);
+    return launch_sweep<KIND_BWD, false>(c, P, spec, 4, 5);
 }
 
 // ------------------------------------------------------- Gauss-Seidel projection ----
@@ -618,18 +748,13 @@ __global__ void __launch_bounds__(1024) k_scalar_gs(const double *__restrict__ p
 static int enqueue_gs_sweep(ifl_ctx *c, double scale) {
     SweepParams P;
     memset(&P, 0, sizeof P);
-    P.nt = 3;
-    P.nst = 5;
-    P.swept = 0;
     P.gated = 1;
     P.scale = scale;
-    P.t[0] = tile(c->p, 1, 0, 1);
-    P.t[1] = tile(c->p, 1, 0, 0);
-    P.t[1].row_shift = 1; // the row below, old values (v2:264)
-    P.t[2] = tile(c->r, 1, 0, 0);
+    // tile 1 is p again, fetched one row further down: the old values of the row below (v2:264)
+    const TileSpec spec[3] = {{&c->p, 1, 0, 1}, {&c->p, 1, 1, 0}, {&c->r, 1, 0, 0}};
     P.partials = c->partials;
     c->n_partials = (c->H + 31) / 32;
-    int rc = launch_sweep<KIND_GS, false>(c, P);
+    int rc = launch_sweep<KIND_GS, false>(c, P, spec, 3, 5);
     if (rc != IFL_OK) return rc;
     ProfScope ps_(c, IFL_K_SCALAR);
     k_scalar_gs<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal);

@@ -1,0 +1,31 @@
+"""Strip timeline of one backward MIC(0) sweep at SIZE^2 (diagnostics for sweep_kernels.cu):
+prints per-strip start lag and duration, from which the step time T (cycles per column
+step) and the strip-to-strip lag L follow."""
+import importlib
+import sys
+import os
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ifl = importlib.import_module("incremental-fluids_b200")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+s = ifl.FluidSolver(n, n, 0.1, version=3)
+s.buildPressureMatrix(0.005)
+s.buildPreconditioner()
+s.set("r", np.random.default_rng(0).uniform(-1, 1, n * n))
+for _ in range(3):
+    s.applyPreconditioner("z", "r")
+t = s.sweep_times(lambda: s.applyPreconditioner("z", "r")).astype(np.int64)
+t0 = t[:, 0].min()
+start, end = t[:, 0] - t0, t[:, 1] - t0
+dur = end - start
+steps = n + 31
+print("strips %d, columns %d" % (len(t), n))
+print("strip 0 duration %.1f us -> %.1f ns/step" % (dur[0] / 1e3, dur[0] / steps))
+print("total %.1f us" % (end.max() / 1e3))
+print("end-to-end lag between consecutive strips (us): mean %.2f  min %.2f  max %.2f" %
+      (np.diff(end).mean() / 1e3, np.diff(end).min() / 1e3, np.diff(end).max() / 1e3))
+print("start lag (us): mean %.2f" % (np.diff(start).mean() / 1e3))
+for i in list(range(0, len(t), max(1, len(t) // 16))):
+    print("  strip %3d start %8.1f end %8.1f dur %8.1f us" % (i, start[i] / 1e3, end[i] / 1e3, dur[i] / 1e3))
