@@ -158,6 +158,40 @@ __device__ __forceinline__ bool ll_load(const uint4 *src, unsigned epoch, double
     return b == epoch && d == epoch;
 }
 
+// Shared-memory accessors on 32-bit shared-space byte addresses: the per-step address is
+// `selected base + compile-time offset`, which ptxas folds into the instruction's
+// immediate field, so a step spends one ISETP + one SEL on addressing.
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_f64_if(double &v, uint32_t a, bool pred) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p ld.shared.f64 %0, [%1];\n\t"
+        "}"
+        : "+d"(v)
+        : "r"(a), "r"((unsigned)pred)
+        : "memory");
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ double sel_f64(bool pred, double a, double b) { // pred ? a : b, one select deep
+    double r;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "selp.f64 %0, %1, %2, p;\n\t"
+        "}"
+        : "=d"(r)
+        : "d"(a), "d"(b), "r"((unsigned)pred));
+    return r;
+}
+
 // ---------------------------------------------------------------- compute warp ----
 template <int KIND>
 struct Geo {
@@ -181,36 +215,37 @@ struct Ops {
     double a, b, c, d, e, halo;
 };
 
-// p -> tile 0, this lane's row, this step's column; tile k sits k*TILE_DOUBLES further.
-// p_right (KIND_GS only) -> tile 0, same row, next logical column (may be in the next block).
-// ph (lane 0 only) -> the swept variable of the upstream strip's last row at this column.
+// p -> tile 0, this lane's row, this step's column (shared-space byte address); tile k
+// sits k*TILE_BYTES further.  p_right (KIND_GS only) -> tile 0, same row, next logical
+// column (may be in the next block).  ph (lane 0 only) -> the swept variable of the
+// upstream strip's last row at this column.
 template <int KIND, bool DOT>
-__device__ __forceinline__ void fetch(Ops &o, const double *p, const double *p_right, const double *ph, int lane) {
-    constexpr int UP = Geo<KIND>::UP_OFF;
+__device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint32_t ph, int lane) {
+    constexpr int UP = Geo<KIND>::UP_OFF * 8;
     if (KIND == KIND_GS) {
-        o.a = p[0];                // p (old)  own cell, updated in place
-        o.b = p_right[0];          // p (old)  right cell
-        o.c = p[1 * TILE_DOUBLES]; // p (old)  lower cell (tile 1 = p fetched one row down)
-        o.d = p[2 * TILE_DOUBLES]; // r        own cell
+        o.a = lds_f64(p);                  // p (old)  own cell, updated in place
+        o.b = lds_f64(p_right);            // p (old)  right cell
+        o.c = lds_f64(p + 1 * TILE_BYTES); // p (old)  lower cell (tile 1 = p fetched one row down)
+        o.d = lds_f64(p + 2 * TILE_BYTES); // r        own cell
     } else if (KIND == KIND_FWD) {
-        o.a = p[0];                     // a (rhs)  own cell
-        o.b = p[1 * TILE_DOUBLES];      // cx       own cell (carried to the next step)
-        o.c = p[2 * TILE_DOUBLES + UP]; // cy       upper cell
-        o.d = p[3 * TILE_DOUBLES];      // precon   own cell
+        o.a = lds_f64(p);                       // a (rhs)  own cell
+        o.b = lds_f64(p + 1 * TILE_BYTES);      // cx       own cell (carried to the next step)
+        o.c = lds_f64(p + 2 * TILE_BYTES + UP); // cy       upper cell
+        o.d = lds_f64(p + 3 * TILE_BYTES);      // precon   own cell
     } else if (KIND == KIND_BWD) {
-        o.a = p[0];                         // z (forward result) own cell, updated in place
-        o.b = p[1 * TILE_DOUBLES];          // cx own
-        o.c = p[2 * TILE_DOUBLES];          // cy own
-        o.d = p[3 * TILE_DOUBLES];          // precon own
-        if (DOT) o.e = p[4 * TILE_DOUBLES]; // r own
+        o.a = lds_f64(p);                            // z (forward result) own cell, updated in place
+        o.b = lds_f64(p + 1 * TILE_BYTES);           // cx own
+        o.c = lds_f64(p + 2 * TILE_BYTES);           // cy own
+        o.d = lds_f64(p + 3 * TILE_BYTES);           // precon own
+        if (DOT) o.e = lds_f64(p + 4 * TILE_BYTES);  // r own
     } else {
-        o.a = p[0];                     // aDiag own
-        o.b = p[1 * TILE_DOUBLES];      // aPlusX own
-        o.c = p[2 * TILE_DOUBLES];      // aPlusY own
-        o.d = p[1 * TILE_DOUBLES + UP]; // aPlusX upper
-        o.e = p[2 * TILE_DOUBLES + UP]; // aPlusY upper
+        o.a = lds_f64(p);                       // aDiag own
+        o.b = lds_f64(p + 1 * TILE_BYTES);      // aPlusX own
+        o.c = lds_f64(p + 2 * TILE_BYTES);      // aPlusY own
+        o.d = lds_f64(p + 1 * TILE_BYTES + UP); // aPlusX upper
+        o.e = lds_f64(p + 2 * TILE_BYTES + UP); // aPlusY upper
     }
-    if (lane == 0) o.halo = ph[0];
+    lds_f64_if(o.halo, ph, lane == 0);
 }
 
 // Per-lane constants of a Gauss-Seidel sweep.
@@ -225,7 +260,7 @@ struct GsConst {
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
 // logical column.  Returns the new value of the swept variable; writes results into the tile.
 template <int KIND, bool DOT>
-__device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, double *p, int c, const GsConst &gs) {
+__device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint32_t p, int c, const GsConst &gs) {
     double znew;
     if (KIND == KIND_GS) {
         // Missing neighbours read +0.0 (left: initial carry, up: zeroed halo row, right:
@@ -240,18 +275,18 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, doubl
         const double diag = cnt == 4 ? gs.d4 : (cnt == 3 ? gs.d3 : (cnt == 2 ? gs.d2 : gs.d1));
         znew = (o.d - off) / diag;       // v2:267
         if (gs.yvalid && c < gs.W) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
-        p[0] = znew;                     // v2:271
+        sts_f64(p, znew);                // v2:271
     } else if (KIND == KIND_FWD) {
         double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
         t = t - o.c * up;                  // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
         znew = t * o.d;                    // v3:285
-        p[4 * TILE_DOUBLES] = znew;
+        sts_f64(p + 4 * TILE_BYTES, znew);
         cr.c1 = o.b;
     } else if (KIND == KIND_BWD) {
         double t = o.a - o.b * cr.zprev; // v3:297  t -= aPlusX[idx]*precon[idx]*dst[idx+1]
         t = t - o.c * up;                // v3:299  t -= aPlusY[idx]*precon[idx]*dst[idx+w]
         znew = t * o.d;                  // v3:301
-        p[0] = znew;
+        sts_f64(p, znew);
         if (DOT) cr.acc += znew * o.e;   // v3:310 (partial)
     } else {
         const double tau = 0.97, sigma = 0.25; // v3:248-249
@@ -262,9 +297,9 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, doubl
         if (e < sigma * o.a) e = o.a;                    // v3:266-267
         znew = 1.0 / sqrt(e);                            // v3:269
         const double cxo = o.b * znew, cyo = o.c * znew;
-        p[3 * TILE_DOUBLES] = znew;
-        p[4 * TILE_DOUBLES] = cxo;
-        p[5 * TILE_DOUBLES] = cyo;
+        sts_f64(p + 3 * TILE_BYTES, znew);
+        sts_f64(p + 4 * TILE_BYTES, cxo);
+        sts_f64(p + 5 * TILE_BYTES, cyo);
         cr.c1 = cxo;
         cr.c2 = cyo;
     }
@@ -278,18 +313,18 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, doubl
 // its skew, so the address is always `base + DIR*j` and j folds into the instruction's
 // immediate offset.  Positions that do not exist (first / last macro-step) alias valid
 // memory and are never used.
-struct LaneBases {
-    double *A; // block m
-    double *B; // block m-1
-    double *N; // block m+1
+struct LaneBases { // shared-space byte addresses
+    uint32_t A; // block m
+    uint32_t B; // block m-1
+    uint32_t N; // block m+1
 };
 
 template <int KIND>
-__device__ __forceinline__ double *pos(const LaneBases &lb, int j, int lane) {
-    constexpr int DIR = Geo<KIND>::BWD ? -1 : 1;
-    double *base = (lane > j) ? lb.B : lb.A;
+__device__ __forceinline__ uint32_t pos(const LaneBases &lb, int j, int lane) {
+    constexpr int DIR = Geo<KIND>::BWD ? -8 : 8;
+    uint32_t base = (lane > j) ? lb.B : lb.A;
     if (j >= 32) base = (lane <= j - 32) ? lb.N : base; // j is a compile-time constant
-    return base + DIR * j;
+    return base + (uint32_t)(DIR * j);
 }
 
 // One macro-step = 32 steps of the skewed warp.  During macro-step m lane t works on
@@ -300,14 +335,15 @@ __device__ __forceinline__ double *pos(const LaneBases &lb, int j, int lane) {
 // (lanes that have not entered the strip idle), 2 last macro-step (lanes that have left
 // the strip idle).
 template <int KIND, bool DOT, int EDGE>
-__device__ __forceinline__ void macro_step(const LaneBases &lb, const double *h_cur, const double *h_next,
+__device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next,
                                            uint64_t *full_next, unsigned parity_next, bool wait_next, int m, int lane,
                                            Carry &cr, Ops &ops, uint4 *handoff_row, bool publish, unsigned epoch,
                                            const GsConst &gs, volatile int *dead, SolveScalars *scal) {
     typedef Geo<KIND> G;
-    constexpr int DIR = G::BWD ? -1 : 1;
+    constexpr int DIR = G::BWD ? -8 : 8;
     // Gauss-Seidel also reads the right neighbour, i.e. looks one column further ahead
     constexpr int WAIT_KK = (KIND == KIND_GS) ? 30 : 31;
+    uint32_t p = pos<KIND>(lb, 0, lane);
 #pragma unroll
     for (int kk = 0; kk < 32; kk++) {
         if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next, dead, scal); // lane 0 is about to touch block m+1
@@ -315,10 +351,10 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, const double *h_
         double up = __shfl_up_sync(0xffffffffu, cr.zprev, 1);
         // ---- operands of step kk+1, in the shadow of the shuffle
         Ops nxt;
+        const uint32_t pn = pos<KIND>(lb, kk + 1, lane);
         {
-            const double *pn = pos<KIND>(lb, kk + 1, lane);
-            const double *pr = (KIND == KIND_GS) ? pos<KIND>(lb, kk + 2, lane) : pn;
-            const double *ph = (kk + 1 < 32) ? h_cur + DIR * (kk + 1) : h_next + DIR * (kk + 1 - 32);
+            const uint32_t pr = (KIND == KIND_GS) ? pos<KIND>(lb, kk + 2, lane) : pn;
+            const uint32_t ph = (kk + 1 < 32) ? h_cur + (uint32_t)(DIR * (kk + 1)) : h_next + (uint32_t)(DIR * (kk + 1 - 32));
             nxt.halo = ops.halo;
             fetch<KIND, DOT>(nxt, pn, pr, ph, lane);
             if (KIND == KIND_GS && !(32 * m + kk + 2 - lane < gs.W)) nxt.b = 0.0; // no right neighbour (v2:258)
@@ -326,13 +362,13 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, const double *h_
         // ---- this step
         const int d0 = kk - lane;
         const bool active = (EDGE == 0) ? true : (EDGE == 1 ? d0 >= 0 : d0 < 0);
-        double *p = pos<KIND>(lb, kk, lane);
-        if (lane == 0) up = ops.halo;
+        up = sel_f64(lane == 0, ops.halo, up);
         if (active) {
             const double z = cell<KIND, DOT>(ops, cr, up, p, 32 * m + d0, gs);
             ll_store(handoff_row + 32 * m + d0, z, epoch, publish && lane == 31);
         }
         ops = nxt;
+        p = pn;
     }
 }
 
@@ -340,7 +376,7 @@ template <int KIND, bool DOT>
 __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *full, uint64_t *done, int sj,
                              int lane, volatile int *dead) {
     typedef Geo<KIND> G;
-    constexpr int DIR = G::BWD ? -1 : 1;
+    constexpr int DIR = G::BWD ? -8 : 8; // bytes per logical column step
     constexpr int COL0 = G::BWD ? 31 : 0; // tile column of logical in-block column 0
     Carry cr;
     cr.zprev = 0.0;
@@ -350,8 +386,10 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     const bool publish = sj + 1 < P.nby;
     uint4 *handoff_row = P.handoff + (size_t)sj * P.nbx * 32;
     const int nst = P.nst, nbx = P.nbx;
-    const int stage_doubles = P.nt * TILE_DOUBLES;
-    double *row0 = smem + G::lane_row(lane) * TP + COL0; // this lane's row in tile 0 of stage 0, logical column 0
+    const uint32_t stage_bytes = (uint32_t)P.nt * TILE_BYTES;
+    // this lane's row in tile 0 of stage 0 at logical column 0, and the hand-off row of stage 0
+    const uint32_t row0 = smem_u32(smem) + (uint32_t)(G::lane_row(lane) * TP + COL0) * 8u;
+    const uint32_t halo0 = smem_u32(halo_s) + (uint32_t)COL0 * 8u;
     GsConst gs;
     gs.scale = P.scale;
     gs.d1 = 0.0 + P.scale;
@@ -368,34 +406,35 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
     mbar_wait(&full[0], 0, dead, P.scal);
-    fetch<KIND, DOT>(ops, row0, row0 + DIR, halo_s + COL0, lane);
+    fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
     if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
     unsigned par_next = 0;                        // parity of full[sn] for block m+1
     for (int m = 0; m <= nbx; m++) {
         const bool has_next = m + 1 < nbx;
-        double *s_prev = row0 + sp * stage_doubles;
-        double *s_cur = row0 + sc * stage_doubles;
-        double *s_next = row0 + sn * stage_doubles;
-        const double *h_cur = halo_s + sc * 32 + COL0;
-        const double *h_next = halo_s + (has_next ? sn : sc) * 32 + COL0;
+        const uint32_t s_prev = row0 + sp * stage_bytes;
+        const uint32_t s_cur = row0 + sc * stage_bytes;
+        const uint32_t s_next = row0 + sn * stage_bytes;
+        const uint32_t h_cur = halo0 + sc * 256u;
+        const uint32_t h_next = halo0 + (has_next ? sn : sc) * 256u;
+        const uint32_t skew = (uint32_t)(DIR * lane), blk = (uint32_t)(DIR * 32);
         LaneBases lb;
         if (m == 0) { // no block m-1: idle lanes alias block 0
-            lb.A = s_cur - DIR * lane;
+            lb.A = s_cur - skew;
             lb.B = lb.A;
-            lb.N = has_next ? s_next - DIR * (32 + lane) : lb.A;
+            lb.N = has_next ? s_next - blk - skew : lb.A;
             macro_step<KIND, DOT, 1>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
                                      publish, P.epoch, gs, dead, P.scal);
         } else if (m == nbx) { // no block m: idle lanes alias block m-1
-            lb.B = s_prev + DIR * (32 - lane);
-            lb.A = s_prev - DIR * lane;
+            lb.B = s_prev + blk - skew;
+            lb.A = s_prev - skew;
             lb.N = lb.A;
             macro_step<KIND, DOT, 2>(lb, h_cur, h_next, &full[sn], par_next, false, m, lane, cr, ops, handoff_row,
                                      publish, P.epoch, gs, dead, P.scal);
         } else {
-            lb.A = s_cur - DIR * lane;
-            lb.B = s_prev + DIR * (32 - lane);
-            lb.N = has_next ? s_next - DIR * (32 + lane) : lb.A;
+            lb.A = s_cur - skew;
+            lb.B = s_prev + blk - skew;
+            lb.N = has_next ? s_next - blk - skew : lb.A;
             macro_step<KIND, DOT, 0>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
                                      publish, P.epoch, gs, dead, P.scal);
         }
