@@ -179,14 +179,14 @@ class FluidSolver:
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     def sweep_times(self, fn):
-        """Runs fn() with strip timing armed; returns ns[strips, 2] of the LAST sweep fn launched."""
+        """Runs fn() with strip timing armed; returns ns[strips, 16] (start, end, 1/8 checkpoints) of the LAST sweep fn launched."""
         self._chk(self.L.ifl_debug_sweep_times(self.ctx, 1, None, 0))
         fn()
-        buf = np.zeros(2 * ((self.h + 31) // 32), dtype=np.uint64)
+        buf = np.zeros(16 * ((self.h + 31) // 32), dtype=np.uint64)
         n = self.L.ifl_debug_sweep_times(self.ctx, 0, buf.ctypes.data, buf.size)
         if n < 0:
             self._chk(n)
-        return buf.reshape(-1, 2)
+        return buf.reshape(-1, 16)
 
     # ---- private hot-path methods of the reference class
     def buildRhs(self):

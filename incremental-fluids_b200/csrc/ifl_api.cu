@@ -240,12 +240,12 @@ int ifl_debug_sweep_times(ifl_ctx *c, int arm, unsigned long long *out_ns, int c
         return IFL_OK;
     }
     c->sweep_times = nullptr;
-    if (!out_ns || capacity < 2 * c->n_strips) {
-        set_error("ifl_debug_sweep_times: need room for %d values", 2 * c->n_strips);
+    if (!out_ns || capacity < 16 * c->n_strips) {
+        set_error("ifl_debug_sweep_times: need room for %d values", 16 * c->n_strips);
         return IFL_E_ARG;
     }
     IFL_CUDA(cudaStreamSynchronize(c->stream));
-    IFL_CUDA(cudaMemcpy(out_ns, c->sweep_times_buf, (size_t)2 * c->n_strips * sizeof(unsigned long long),
+    IFL_CUDA(cudaMemcpy(out_ns, c->sweep_times_buf, (size_t)16 * c->n_strips * sizeof(unsigned long long),
                         cudaMemcpyDeviceToHost));
     return c->n_strips;
 }

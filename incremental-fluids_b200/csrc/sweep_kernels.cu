@@ -19,7 +19,9 @@
 //     walks it in 32-column blocks.  Strips are handed out by an atomic ticket, so a
 //     running CTA only ever waits on strips that are already running or finished
 //     (no co-residency assumption, no deadlock).
-//   * Inside the CTA three warps are specialised:
+//   * Inside the CTA five warps are specialised (compute, TMA loader, storer, publisher,
+//     hand-off poller; the last two exist so that the compute warp issues nothing but
+//     the recurrence itself):
 //       warp 0 (compute): lane t owns row t of the strip and is skewed t columns
 //         behind lane t-1, i.e. the warp is one anti-diagonal.  The left neighbour is
 //         the lane's own previous value (register), the upper neighbour arrives by
@@ -60,6 +62,7 @@ constexpr int TILE_DOUBLES = TROWS * TP;     // 1056
 constexpr int TILE_BYTES = TILE_DOUBLES * 8; // 8448 (multiple of 128)
 constexpr int MAX_TILES = 6;
 constexpr int MAX_STAGES = 8;
+constexpr int HG = 8; // hand-off granularity in columns (publisher and consumer side)
 constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
 constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
 
@@ -139,17 +142,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // NCCL-LL style message: {lo, epoch, hi, epoch} in one 16-byte store / load.
-__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch, bool pred) {
-    // predicated inside the asm so that the per-step publish needs no branch
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch) {
     const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.u32 p, %5, 0;\n\t"
-        "@p st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t"
-        "}" ::"l"(dst),
-        "r"(lo), "r"(epoch), "r"(hi), "r"(epoch), "r"((unsigned)pred)
-        : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
+                 : "memory");
 }
 __device__ __forceinline__ bool ll_load(const uint4 *src, unsigned epoch, double &v) {
     unsigned a, b, c, d;
@@ -179,6 +175,26 @@ __device__ __forceinline__ void lds_f64_if(double &v, uint32_t a, bool pred) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32_volatile(uint32_t a, unsigned v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32_volatile(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// Bounded spin until the shared counter at `a` reaches `need`.
+__device__ __forceinline__ void wait_counter(uint32_t a, unsigned need, volatile int *dead, SolveScalars *scal) {
+    if (lds_u32_volatile(a) >= need) return;
+    unsigned n = 0;
+    while (lds_u32_volatile(a) < need) {
+        if (++n > WATCHDOG_POLLS || *dead) {
+            *dead = 1;
+            scal->watchdog = 1;
+            return;
+        }
+    }
 }
 __device__ __forceinline__ double sel_f64(bool pred, double a, double b) { // pred ? a : b, one select deep
     double r;
@@ -237,7 +253,6 @@ __device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint
         o.b = lds_f64(p + 1 * TILE_BYTES);           // cx own
         o.c = lds_f64(p + 2 * TILE_BYTES);           // cy own
         o.d = lds_f64(p + 3 * TILE_BYTES);           // precon own
-        if (DOT) o.e = lds_f64(p + 4 * TILE_BYTES);  // r own
     } else {
         o.a = lds_f64(p);                       // aDiag own
         o.b = lds_f64(p + 1 * TILE_BYTES);      // aPlusX own
@@ -245,7 +260,7 @@ __device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint
         o.d = lds_f64(p + 1 * TILE_BYTES + UP); // aPlusX upper
         o.e = lds_f64(p + 2 * TILE_BYTES + UP); // aPlusY upper
     }
-    lds_f64_if(o.halo, ph, lane == 0);
+    o.halo = lds_f64(ph); // same address in every lane (broadcast); only lane 0 uses it
 }
 
 // Per-lane constants of a Gauss-Seidel sweep.
@@ -255,6 +270,7 @@ struct GsConst {
     int ycnt;              // (y > 0) + (y < H-1) of this lane's row
     int yvalid;            // y < H
     int W;
+    int ncols;             // padded sweep width (32 * nbx)
 };
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
@@ -286,8 +302,7 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         double t = o.a - o.b * cr.zprev; // v3:297  t -= aPlusX[idx]*precon[idx]*dst[idx+1]
         t = t - o.c * up;                // v3:299  t -= aPlusY[idx]*precon[idx]*dst[idx+w]
         znew = t * o.d;                  // v3:301
-        sts_f64(p, znew);
-        if (DOT) cr.acc += znew * o.e;   // v3:310 (partial)
+        sts_f64(p, znew);                // (z.r of v3:374 is accumulated by the storer warp)
     } else {
         const double tau = 0.97, sigma = 0.25; // v3:248-249
         double e = o.a;
@@ -337,8 +352,9 @@ __device__ __forceinline__ uint32_t pos(const LaneBases &lb, int j, int lane) {
 template <int KIND, bool DOT, int EDGE>
 __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next,
                                            uint64_t *full_next, unsigned parity_next, bool wait_next, int m, int lane,
-                                           Carry &cr, Ops &ops, uint4 *handoff_row, bool publish, unsigned epoch,
-                                           const GsConst &gs, volatile int *dead, SolveScalars *scal) {
+                                           Carry &cr, Ops &ops, uint32_t progress_addr, uint32_t halo_cols_addr,
+                                           bool has_up, const GsConst &gs, volatile int *dead, SolveScalars *scal,
+                                           unsigned long long *times, int probe) {
     typedef Geo<KIND> G;
     constexpr int DIR = G::BWD ? -8 : 8;
     // Gauss-Seidel also reads the right neighbour, i.e. looks one column further ahead
@@ -347,6 +363,11 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
 #pragma unroll
     for (int kk = 0; kk < 32; kk++) {
         if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next, dead, scal); // lane 0 is about to touch block m+1
+        // lane 0 is about to fetch the first hand-off value of the next group of HG columns
+        if (((kk + 1) % HG) == 0 && has_up && EDGE != 2) {
+            wait_counter(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
+            if (times && lane == 0 && 32 * m + kk + 1 + HG == probe) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(times[14]));
+        }
         // ---- critical path first: the upper neighbour's value of the previous step
         double up = __shfl_up_sync(0xffffffffu, cr.zprev, 1);
         // ---- operands of step kk+1, in the shadow of the shuffle
@@ -355,7 +376,6 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         {
             const uint32_t pr = (KIND == KIND_GS) ? pos<KIND>(lb, kk + 2, lane) : pn;
             const uint32_t ph = (kk + 1 < 32) ? h_cur + (uint32_t)(DIR * (kk + 1)) : h_next + (uint32_t)(DIR * (kk + 1 - 32));
-            nxt.halo = ops.halo;
             fetch<KIND, DOT>(nxt, pn, pr, ph, lane);
             if (KIND == KIND_GS && !(32 * m + kk + 2 - lane < gs.W)) nxt.b = 0.0; // no right neighbour (v2:258)
         }
@@ -364,8 +384,12 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         const bool active = (EDGE == 0) ? true : (EDGE == 1 ? d0 >= 0 : d0 < 0);
         up = sel_f64(lane == 0, ops.halo, up);
         if (active) {
-            const double z = cell<KIND, DOT>(ops, cr, up, p, 32 * m + d0, gs);
-            ll_store(handoff_row + 32 * m + d0, z, epoch, publish && lane == 31);
+            cell<KIND, DOT>(ops, cr, up, p, 32 * m + d0, gs);
+        }
+        // the strip's last row (lane 31) has just completed another group of HG columns
+        if (((kk + 2) % HG) == 0) {
+            sts_u32_volatile(progress_addr, (unsigned)imax(32 * m + kk - 30, 0));
+            if (times && lane == 0 && 32 * m + kk - 30 == probe) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(times[11]));
         }
         ops = nxt;
         p = pn;
@@ -374,7 +398,7 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
 
 template <int KIND, bool DOT>
 __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *full, uint64_t *done, int sj,
-                             int lane, volatile int *dead) {
+                             int lane, volatile int *dead, unsigned *counters) {
     typedef Geo<KIND> G;
     constexpr int DIR = G::BWD ? -8 : 8; // bytes per logical column step
     constexpr int COL0 = G::BWD ? 31 : 0; // tile column of logical in-block column 0
@@ -383,8 +407,8 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     cr.c1 = 0.0;
     cr.c2 = 0.0;
     cr.acc = 0.0;
-    const bool publish = sj + 1 < P.nby;
-    uint4 *handoff_row = P.handoff + (size_t)sj * P.nbx * 32;
+    const bool has_up = sj > 0;
+    const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
     const int nst = P.nst, nbx = P.nbx;
     const uint32_t stage_bytes = (uint32_t)P.nt * TILE_BYTES;
     // this lane's row in tile 0 of stage 0 at logical column 0, and the hand-off row of stage 0
@@ -401,16 +425,25 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.ycnt = (y > 0 ? 1 : 0) + (y < P.H - 1 ? 1 : 0);
         gs.yvalid = y < P.H ? 1 : 0;
         gs.W = P.W;
+        gs.ncols = P.nbx * 32;
     }
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
     mbar_wait(&full[0], 0, dead, P.scal);
+    if (has_up) wait_counter(halo_cols_addr, HG, dead, P.scal);
     fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
     if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
     unsigned par_next = 0;                        // parity of full[sn] for block m+1
+    const int probe = (nbx / 2) * 32; // diagnostics: hand-off timestamps for the group ending at this column
+    const int ck = (nbx + 7) / 8; // diagnostics: a timestamp every nbx/8 macro-steps
     for (int m = 0; m <= nbx; m++) {
+        if (P.times && lane == 0 && (m % ck) == 0 && m / ck < 12) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt));
+            P.times[16 * sj + 2 + m / ck] = tt;
+        }
         const bool has_next = m + 1 < nbx;
         const uint32_t s_prev = row0 + sp * stage_bytes;
         const uint32_t s_cur = row0 + sc * stage_bytes;
@@ -423,20 +456,20 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
             lb.A = s_cur - skew;
             lb.B = lb.A;
             lb.N = has_next ? s_next - blk - skew : lb.A;
-            macro_step<KIND, DOT, 1>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs, dead, P.scal);
+            macro_step<KIND, DOT, 1>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, progress_addr,
+                                     halo_cols_addr, has_up, gs, dead, P.scal, P.times ? P.times + 16 * sj : nullptr, probe);
         } else if (m == nbx) { // no block m: idle lanes alias block m-1
             lb.B = s_prev + blk - skew;
             lb.A = s_prev - skew;
             lb.N = lb.A;
-            macro_step<KIND, DOT, 2>(lb, h_cur, h_next, &full[sn], par_next, false, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs, dead, P.scal);
+            macro_step<KIND, DOT, 2>(lb, h_cur, h_next, &full[sn], par_next, false, m, lane, cr, ops, progress_addr,
+                                     halo_cols_addr, has_up, gs, dead, P.scal, P.times ? P.times + 16 * sj : nullptr, probe);
         } else {
             lb.A = s_cur - skew;
             lb.B = s_prev + blk - skew;
             lb.N = has_next ? s_next - blk - skew : lb.A;
-            macro_step<KIND, DOT, 0>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, handoff_row,
-                                     publish, P.epoch, gs, dead, P.scal);
+            macro_step<KIND, DOT, 0>(lb, h_cur, h_next, &full[sn], par_next, has_next, m, lane, cr, ops, progress_addr,
+                                     halo_cols_addr, has_up, gs, dead, P.scal, P.times ? P.times + 16 * sj : nullptr, probe);
         }
         if (m >= 1) {
             // block m-1 is complete in smem: hand it to the storer (and, through it, the loader)
@@ -455,71 +488,89 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     if (KIND == KIND_GS) {
         const double s = warp_max(cr.acc);
         if (lane == 0) P.partials[sj] = s;
-    } else if (DOT) {
-        const double s = warp_sum(cr.acc);
-        if (lane == 0) P.partials[sj] = s;
     }
 }
 
 // ----------------------------------------------------------------- loader warp ----
-// Keeps the TMA ring `nst-3` blocks ahead of the block whose hand-off row it is
-// currently waiting for.  The compute warp releases block j only at the end of
-// macro-step j+1, and inside that macro-step it already waits for block j+2; block j
-// therefore drains only after the hand-off row of block j+2 has been delivered, and a
-// window deeper than nst-3 would make the loader wait for a stage that cannot drain.
+// Keeps the TMA ring `nst-3` blocks ahead of the compute warp.  The compute warp releases
+// block j only at the end of macro-step j+1, and inside that macro-step it already waits
+// for block j+2; a window deeper than nst-3 would wait for a stage that cannot drain.
 template <int KIND>
-__device__ void loader_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *full, uint64_t *empty, int sj,
-                            int lane, volatile int *dead) {
+__device__ void loader_warp(const SweepParams &P, double *smem, uint64_t *full, uint64_t *empty, int sj, int lane,
+                            volatile int *dead) {
     typedef Geo<KIND> G;
+    if (lane != 0) return;
     const int nst = P.nst, nbx = P.nbx;
     const int stage_doubles = P.nt * TILE_DOUBLES;
     const int ty = G::BWD ? (P.nby - 1 - sj) : sj; // memory tile row of this strip
     const int box_y = G::BWD ? ty * 32 : ty * 32 - 1;
-    const bool has_up = sj > 0;
     int nload = 0;
     for (int k = 0; k < P.nt; k++) nload += P.t[k].load ? 1 : 0;
     const unsigned bytes = (unsigned)nload * TILE_BYTES;
-    const uint4 *up_row = P.handoff + (size_t)(has_up ? sj - 1 : 0) * nbx * 32;
-    const int ahead = nst - 3;
-    unsigned polls = 0;
-    int issued = 0;
-
     for (int m = 0; m < nbx; m++) {
-        while (issued < nbx && issued <= m + ahead) {
-            const int st = issued % nst;
-            if (issued >= nst) mbar_wait(&empty[st], ((issued / nst) - 1) & 1, dead, P.scal);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&full[st], bytes);
-                const int box_x = (G::BWD ? (nbx - 1 - issued) : issued) * 32;
-                double *stage = smem + st * stage_doubles;
-                for (int k = 0; k < P.nt; k++)
-                    if (P.t[k].load)
-                        tma_load_2d(stage + k * TILE_DOUBLES, &P.map[k], box_x, box_y + P.t[k].row_shift, &full[st]);
-            }
-            __syncwarp();
-            issued++;
-        }
-        // swept variable of the upstream strip's last row (LL hand-off) -> halo_s[stage]
         const int st = m % nst;
-        if (has_up) {
-            double v = 0.0;
-            const uint4 *src = up_row + (size_t)m * 32 + lane;
-            while (!ll_load(src, P.epoch, v)) {
-                if (++polls > WATCHDOG_POLLS || *dead) {
+        if (m >= nst) mbar_wait(&empty[st], ((m / nst) - 1) & 1, dead, P.scal);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        const int box_x = (G::BWD ? (nbx - 1 - m) : m) * 32;
+        double *stage = smem + st * stage_doubles;
+        for (int k = 0; k < P.nt; k++)
+            if (P.t[k].load)
+                tma_load_2d(stage + k * TILE_DOUBLES, &P.map[k], box_x, box_y + P.t[k].row_shift, &full[st]);
+    }
+}
+
+// ----------------------------------------------------------------- poller warp ----
+// Receives the swept variable of the upstream strip's last row (LL hand-off) into
+// halo_s[stage] and releases the compute warp group by group (HG columns) through
+// counters[1].  It runs independently of the TMA ring; it only has to stay less than a
+// ring's worth of blocks ahead of the strip's own last row (counters[0]) so that a
+// hand-off row is never overwritten while lane 0 may still read it.
+template <int KIND>
+__device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int lane, volatile int *dead,
+                            unsigned *counters) {
+    typedef Geo<KIND> G;
+    const int nst = P.nst, nbx = P.nbx;
+    const uint4 *up_row = P.handoff + (size_t)(sj - 1) * nbx * 32;
+    const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
+    unsigned polls = 0;
+    for (int m = 0; m < nbx; m++) {
+        const int st = m % nst;
+        if (m >= nst) wait_counter(progress_addr, (unsigned)(32 * (m - nst + 1)), dead, P.scal);
+        const uint4 *src = up_row + (size_t)m * 32 + lane;
+        bool have = false;
+        unsigned published = 0; // columns of this block already released
+        while (published < 32) {
+            if (!have) {
+                double v;
+                if (ll_load(src, P.epoch, v)) {
+                    halo_s[st * 32 + G::tcol(lane)] = v;
+                    have = true;
+                    polls = 0;
+                } else if (++polls > WATCHDOG_POLLS || *dead) {
                     *dead = 1;
                     P.scal->watchdog = 1;
-                    break;
+                    have = true;
                 }
             }
-            halo_s[st * 32 + G::tcol(lane)] = v;
+            const unsigned mask = __ballot_sync(0xffffffffu, have);
+            const unsigned lead = (mask == 0xffffffffu) ? 32u : (unsigned)(__ffs(~mask) - 1); // leading valid columns
+            const unsigned groups = lead / HG * HG;
+            if (groups > published) {
+                __threadfence_block(); // halo_s values before the counter
+                if (lane == 0) sts_u32_volatile(halo_cols_addr, (unsigned)(32 * m) + groups);
+                if (P.times && lane == 0 && 32 * m + (int)published < (nbx / 2) * 32 && 32 * m + (int)groups >= (nbx / 2) * 32)
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(P.times[16 * sj + 13]));
+                published = groups;
+            }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
     }
 }
 
 // ----------------------------------------------------------------- storer warp ----
-template <int KIND>
+// Drains finished result tiles and, for the backward solve of the PCG loop, folds in
+// dotProduct(z, r) (v3:374): each lane accumulates its cells in a fixed order, the warp
+// sum goes to partials[strip].  Pad cells hold exact zeros and do not perturb the sum.
+template <int KIND, bool DOT>
 __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, uint64_t *empty, int sj, int lane,
                             volatile int *dead) {
     typedef Geo<KIND> G;
@@ -528,6 +579,7 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
     const int ty = G::BWD ? (P.nby - 1 - sj) : sj;
     const int y0 = ty * 32;
     const int half = lane >> 4, l16 = lane & 15;
+    double acc = 0.0;
     for (int m = 0; m < P.nbx; m++) {
         const int st = m % nst;
         double *stage = smem + st * stage_doubles;
@@ -537,6 +589,7 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
         for (int k = 0; k < P.nt; k++) {
             if (!P.t[k].store) continue;
             const double *tile = stage + k * TILE_DOUBLES;
+            const double *rtile = stage + 4 * TILE_DOUBLES; // KIND_BWD with dot: tile 4 holds r
             double *g = P.t[k].p;
 #pragma unroll 4
             for (int i = 0; i < 16; i++) {
@@ -544,6 +597,11 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
                 const int trow = G::BWD ? ry : 1 + ry;
                 const int y = y0 + ry;
                 const double2 v = *reinterpret_cast<const double2 *>(tile + trow * TP + l16 * 2);
+                if (DOT && k == 0) {
+                    const double2 rv = *reinterpret_cast<const double2 *>(rtile + trow * TP + l16 * 2);
+                    acc += v.x * rv.x;
+                    acc += v.y * rv.y;
+                }
                 if (y < P.H) {
                     double *dst = g + x + (size_t)y * P.pitch;
                     if (x + 1 < P.W)
@@ -557,15 +615,73 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
     }
+    if (DOT) {
+        const double sum = warp_sum(acc);
+        if (lane == 0) P.partials[sj] = sum;
+    }
+}
+
+// -------------------------------------------------------------- publisher warp ----
+// Forwards the strip's last row to the downstream strip as LL messages, HG columns at a
+// time, as soon as the compute warp's progress counter says they are final.  It holds
+// each stage until its 32 columns have been sent (second arrival on done[]).
+template <int KIND>
+__device__ void publisher_warp(const SweepParams &P, double *smem, uint64_t *done, int sj, int lane,
+                               volatile int *dead, unsigned *counters) {
+    typedef Geo<KIND> G;
+    const int nst = P.nst;
+    const int stage_doubles = P.nt * TILE_DOUBLES;
+    const int ncols = P.nbx * 32;
+    int swept = (KIND == KIND_FWD) ? 4 : (KIND == KIND_FACTOR ? 3 : 0);
+    const double *last_row = smem + swept * TILE_DOUBLES + G::lane_row(31) * TP; // tile row of the strip's last row
+    uint4 *out = P.handoff + (size_t)sj * ncols;
+    const uint32_t progress_addr = smem_u32(&counters[0]);
+    // The common case is one group of HG columns per round, inside one block: lanes
+    // 0..HG-1 each forward one value.  Block / stage bookkeeping is incremental (no
+    // divisions in the loop).
+    int sent = 0;        // columns forwarded so far
+    int blk_end = 32;    // first column of the next block
+    int st = 0;          // stage of the block `sent` lies in
+    const double *row = last_row; // last row of that stage's swept tile
+    unsigned n = 0;
+    while (sent < ncols) {
+        const int prog = (int)lds_u32_volatile(progress_addr);
+        if (prog > sent) {
+            while (sent < prog) {
+                const int upto = prog < blk_end ? prog : blk_end; // stay inside one block
+                const int c = sent + lane;
+                if (c < upto) ll_store(out + c, row[G::tcol(c & 31)], P.epoch);
+                sent = upto;
+                if (sent == blk_end) { // all 32 columns of this block are out: the stage may drain
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&done[st]);
+                    blk_end += 32;
+                    if (++st == nst) st = 0;
+                    row = last_row + st * stage_doubles;
+                }
+            }
+            if (P.times && lane == 0 && prog == (P.nbx / 2) * 32)
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(P.times[16 * sj + 12]));
+            n = 0;
+        } else if (++n > WATCHDOG_POLLS || *dead) {
+            *dead = 1;
+            P.scal->watchdog = 1;
+            // release every stage so that the other warps can finish
+            for (int b = sent >> 5; b < P.nbx; b++)
+                if (lane == 0) mbar_arrive(&done[b % nst]);
+            return;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------- kernel ----
 template <int KIND, bool DOT>
-__global__ void __launch_bounds__(96, 1) k_sweep(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
     __shared__ int s_strip;
     __shared__ int s_dead;
+    __shared__ unsigned s_counters[2]; // [0] columns finished by the last row, [1] hand-off columns received
     double *smem = reinterpret_cast<double *>(smem_raw);
     double *halo_s = smem + P.nst * P.nt * TILE_DOUBLES; // [nst][32] hand-off rows
     uint64_t *full = bars, *done = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
@@ -574,12 +690,16 @@ __global__ void __launch_bounds__(96, 1) k_sweep(const __grid_constant__ SweepPa
     if (threadIdx.x == 0) {
         // ticket first (keeps the global count consistent even for gated launches)
         const unsigned long long tk = atomicAdd(P.ticket, 1ULL);
-        s_strip = (int)(tk - P.ticket_base);
+        const int sj = (int)(tk - P.ticket_base);
+        s_strip = sj;
         s_dead = 0;
+        s_counters[0] = 0;
+        s_counters[1] = 0;
+        const bool publish = sj + 1 < P.nby;
         for (int i = 0; i < P.nst; i++) {
-            mbar_init(&full[i], 2);  // loader: expect_tx arrive + hand-off arrive
-            mbar_init(&done[i], 1);  // compute warp
-            mbar_init(&empty[i], 1); // storer warp
+            mbar_init(&full[i], 1);                // loader's expect_tx arrival (+ TMA bytes)
+            mbar_init(&done[i], publish ? 2 : 1);  // compute warp (+ publisher warp)
+            mbar_init(&empty[i], 1);               // storer warp
         }
         fence_mbar_init();
     }
@@ -592,18 +712,22 @@ __global__ void __launch_bounds__(96, 1) k_sweep(const __grid_constant__ SweepPa
     if (warp == 0) {
         unsigned long long t0 = 0;
         if (P.times && lane == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-        compute_warp<KIND, DOT>(P, smem, halo_s, full, done, sj, lane, &s_dead);
+        compute_warp<KIND, DOT>(P, smem, halo_s, full, done, sj, lane, &s_dead, s_counters);
         if (P.times && lane == 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-            P.times[2 * sj] = t0;
-            P.times[2 * sj + 1] = t1;
+            P.times[16 * sj] = t0;
+            P.times[16 * sj + 1] = t1;
         }
+    } else if (warp == 1) {
+        loader_warp<KIND>(P, smem, full, empty, sj, lane, &s_dead);
+    } else if (warp == 2) {
+        storer_warp<KIND, DOT>(P, smem, done, empty, sj, lane, &s_dead);
+    } else if (warp == 3) {
+        if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, done, sj, lane, &s_dead, s_counters);
+    } else if (sj > 0) {
+        poller_warp<KIND>(P, halo_s, sj, lane, &s_dead, s_counters);
     }
-    else if (warp == 1)
-        loader_warp<KIND>(P, smem, halo_s, full, empty, sj, lane, &s_dead);
-    else
-        storer_warp<KIND>(P, smem, done, empty, sj, lane, &s_dead);
 }
 
 // ------------------------------------------------------------------- host side ----
@@ -673,7 +797,7 @@ int sweep_init(ifl_ctx *c) {
     IFL_CUDA(cudaMemset(c->handoff, 0, (size_t)nby * nbx * 32 * sizeof(uint4)));
     IFL_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned long long)));
     IFL_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned long long)));
-    IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 2 * sizeof(unsigned long long)));
+    IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 16 * sizeof(unsigned long long)));
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -733,7 +857,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         attr_set[KIND][DOT] = true;
     }
     ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : KIND == KIND_FACTOR ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
-    k_sweep<KIND, DOT><<<P.nby, 96, smem, c->stream>>>(P);
+    k_sweep<KIND, DOT><<<P.nby, 160, smem, c->stream>>>(P);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
