@@ -144,6 +144,26 @@ int ifl_advect(ifl_ctx *ctx, int field, double timestep);
 /* FluidQuantity::flip()  v3:105-107. */
 int ifl_flip(ifl_ctx *ctx, int field);
 
+/* ---- chapters 4+: solid bodies ------------------------------------------------- */
+/* One SolidBody (v4:79-149) as plain data: kind 0 = SolidBox(x,y,sx,sy,theta,vx,vy,vtheta)
+ * (v4:155), 1 = SolidSphere(x,y,s,theta,vx,vy,vtheta) (v4:207; scale_x == scale_y == s). */
+typedef struct {
+    int kind;
+    double pos_x, pos_y, scale_x, scale_y, theta, vel_x, vel_y, vel_theta;
+} ifl_body;
+/* The solver holds its body list by reference and the caller moves the bodies between
+ * updates (v4:960-961): call this after every SolidBody::update(). */
+int ifl_set_bodies(ifl_ctx *ctx, const ifl_body *bodies, int n);
+int ifl_fill_solid_fields(ifl_ctx *ctx, int field);   /* FluidQuantity::fillSolidFields v5:506-559 */
+int ifl_set_boundary_condition(ifl_ctx *ctx);          /* FluidSolver::setBoundaryCondition v4:812-833 */
+int ifl_extrapolate(ifl_ctx *ctx, int field);          /* FluidQuantity::extrapolate v4:551-587 */
+/* Per-quantity solid arrays (dense host layout like ifl_upload): doubles for volume,
+ * normals and phi ((w+1)*(h+1)); bytes for cell and body. */
+typedef enum { IFL_AUX_VOLUME = 0, IFL_AUX_NORMAL_X, IFL_AUX_NORMAL_Y, IFL_AUX_PHI, IFL_AUX_CELL, IFL_AUX_BODY } ifl_aux;
+size_t ifl_aux_elems(const ifl_ctx *ctx, int field, int which);
+int ifl_aux_download(ifl_ctx *ctx, int field, int which, void *host);
+int ifl_aux_upload(ifl_ctx *ctx, int field, int which, const void *host);
+
 /* ---- FluidSolver private hot-path methods ----------------------------------- */
 int ifl_build_rhs(ifl_ctx *ctx);                                         /* v3:208-217 */
 int ifl_build_pressure_matrix(ifl_ctx *ctx, double timestep, double density); /* v3:222-244 */

@@ -16,6 +16,8 @@ from .binding import (  # noqa: F401
     FluidSolver,
     IflError,
     KERNEL_CLASSES,
+    SolidBox,
+    SolidSphere,
     SolveInfo,
     build_library,
     library_path,

@@ -42,6 +42,8 @@ EXPORTS = [
     "ifl_profile", "ifl_profile_read", "ifl_debug_sweep_times",
     "ifl_buf_elems", "ifl_upload", "ifl_download", "ifl_fill",
     "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
+    "ifl_set_bodies", "ifl_fill_solid_fields", "ifl_set_boundary_condition", "ifl_extrapolate",
+    "ifl_aux_elems", "ifl_aux_download", "ifl_aux_upload",
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
     "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
     "ifl_project", "ifl_project_gs", "ifl_apply_pressure",
@@ -91,6 +93,14 @@ def load_library():
     L.ifl_quantity_add_inflow.argtypes = [vp, ci, cd, cd, cd, cd, cd]
     L.ifl_advect.argtypes = [vp, ci, cd]
     L.ifl_flip.argtypes = [vp, ci]
+    L.ifl_set_bodies.argtypes = [vp, vp, ci]
+    L.ifl_fill_solid_fields.argtypes = [vp, ci]
+    L.ifl_set_boundary_condition.argtypes = [vp]
+    L.ifl_extrapolate.argtypes = [vp, ci]
+    L.ifl_aux_elems.restype = ctypes.c_size_t
+    L.ifl_aux_elems.argtypes = [vp, ci, ci]
+    L.ifl_aux_download.argtypes = [vp, ci, ci, vp]
+    L.ifl_aux_upload.argtypes = [vp, ci, ci, vp]
     L.ifl_build_rhs.argtypes = [vp]
     L.ifl_build_pressure_matrix.argtypes = [vp, cd, cd]
     L.ifl_build_preconditioner.argtypes = [vp]
@@ -109,16 +119,61 @@ def load_library():
     return L
 
 
-class FluidSolver:
-    """Drop-in mirror of the reference's FluidSolver for chapters 1-3.
+class BodyRecord(ctypes.Structure):  # struct ifl_body
+    _fields_ = [("kind", ctypes.c_int)] + [(n, ctypes.c_double) for n in
+                ("pos_x", "pos_y", "scale_x", "scale_y", "theta", "vel_x", "vel_y", "vel_theta")]
 
-    FluidSolver(w, h, density)                    v3:401
+
+class SolidBody:
+    """SolidBody (v4:79-149): rigid transform + velocities; update() is the reference's Euler step."""
+    kind = 0
+
+    def __init__(self, x, y, sx, sy, theta, vx, vy, vtheta):
+        self.posX, self.posY, self.scaleX, self.scaleY, self.theta = x, y, sx, sy, theta
+        self.velX, self.velY, self.velTheta = vx, vy, vtheta
+
+    def update(self, timestep):  # v4:140-144
+        self.posX += self.velX * timestep
+        self.posY += self.velY * timestep
+        self.theta += self.velTheta * timestep
+
+    def record(self):
+        return BodyRecord(self.kind, self.posX, self.posY, self.scaleX, self.scaleY, self.theta, self.velX,
+                          self.velY, self.velTheta)
+
+    def as_row(self):
+        """[kind, x, y, sx, sy, theta, vx, vy, vtheta] (flat row format used by test harnesses)."""
+        return [float(self.kind), self.posX, self.posY, self.scaleX, self.scaleY, self.theta, self.velX, self.velY,
+                self.velTheta]
+
+
+class SolidBox(SolidBody):  # v4:152-157
+    kind = 0
+
+
+class SolidSphere(SolidBody):  # v4:204-209: SolidSphere(x, y, s, t, vx, vy, vt)
+    kind = 1
+
+    def __init__(self, x, y, s, theta, vx, vy, vtheta):
+        super().__init__(x, y, s, s, theta, vx, vy, vtheta)
+
+
+AUX = {"volume": 0, "normalX": 1, "normalY": 2, "phi": 3, "cell": 4, "body": 5}
+
+
+class FluidSolver:
+    """Drop-in mirror of the reference's FluidSolver for chapters 1-5.
+
+    FluidSolver(w, h, density[, bodies])          v3:401, v4:836
     addInflow(x, y, w, h, d, u, v)                v3:449
-    update(timestep)                              v3:433
+    update(timestep)                              v3:433, v5:927
     toImage() -> uint8[h*w*4]                     v3:455
+
+    `bodies` is held by reference like in the reference (v4:612): the caller moves the
+    bodies between updates and update() re-reads them.
     """
 
-    def __init__(self, w, h, density, version=3, device=0):
+    def __init__(self, w, h, density, version=3, device=0, bodies=None):
         self.L = load_library()
         self.w, self.h, self.density, self.version = w, h, density, version
         self.hx = 1.0 / min(w, h)
@@ -128,6 +183,37 @@ class FluidSolver:
         self.ctx = ctx
         self.last = None
         self.messages = []  # the stdout lines the reference would have printed
+        self.bodies = bodies if bodies is not None else []
+        if version >= 4:
+            self.syncBodies()
+
+    # ---- chapters 4+
+    def syncBodies(self):
+        arr = (BodyRecord * max(len(self.bodies), 1))(*[b.record() for b in self.bodies])
+        self._chk(self.L.ifl_set_bodies(self.ctx, ctypes.addressof(arr), len(self.bodies)))
+
+    def fillSolidFields(self, field):
+        self._chk(self.L.ifl_fill_solid_fields(self.ctx, FIELD[field]))
+
+    def setBoundaryCondition(self):
+        self._chk(self.L.ifl_set_boundary_condition(self.ctx))
+
+    def extrapolate(self, field):
+        self._chk(self.L.ifl_extrapolate(self.ctx, FIELD[field]))
+
+    def get_aux(self, field, which):
+        n = self.L.ifl_aux_elems(self.ctx, FIELD[field], AUX[which])
+        if n == 0:
+            raise KeyError((field, which))
+        out = np.empty(n, dtype=np.uint8 if which in ("cell", "body") else np.float64)
+        self._chk(self.L.ifl_aux_download(self.ctx, FIELD[field], AUX[which], out.ctypes.data))
+        return out
+
+    def set_aux(self, field, which, arr):
+        a = np.ascontiguousarray(arr, dtype=np.uint8 if which in ("cell", "body") else np.float64).ravel()
+        if a.size != self.L.ifl_aux_elems(self.ctx, FIELD[field], AUX[which]):
+            raise ValueError("size mismatch for %s.%s" % (field, which))
+        self._chk(self.L.ifl_aux_upload(self.ctx, FIELD[field], AUX[which], a.ctypes.data))
 
     def _chk(self, rc):
         if rc != 0:
@@ -258,6 +344,8 @@ class FluidSolver:
 
     def update(self, timestep):
         info = SolveInfo()
+        if self.version >= 4:
+            self.syncBodies()
         self._chk(self.L.ifl_update(self.ctx, timestep, self.density, ctypes.byref(info)))
         self._record(info)
         return self.last

@@ -12,6 +12,7 @@
 // expression keeps the reference's operand order; the library is built with
 // -fmad=false, so results are bit-identical to the CPU reference.
 #include "ifl_internal.cuh"
+#include "solid_geometry.cuh"
 
 namespace ifl {
 
@@ -67,6 +68,45 @@ __device__ __forceinline__ double cerp2(const FieldView &f, double x, double y) 
     return cerp1(q0, q1, q2, q3, y);
 }
 
+// Chapters 4+: advect only fluid cells (the others keep whatever _dst held: SURVEY 3.5
+// quirk 4) and pull back-traced points that land inside a solid onto its surface
+// (FluidQuantity::advect v5:468-485, backProject v5:455-466).
+__global__ void __launch_bounds__(256) k_advect_solid(double *__restrict__ dst, int dst_pitch, FieldView self,
+                                                       const uint8_t *__restrict__ cell, const uint8_t *__restrict__ body,
+                                                       FieldView u, FieldView v, double timestep, double hx,
+                                                       const BodyDev *__restrict__ bodies) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= self.w || iy >= self.h) return;
+    if (cell[ix + (size_t)iy * self.pitch] != CELL_FLUID) return;
+    double x = ix + self.ox;
+    double y = iy + self.oy;
+    const double firstU = lerp2(u, x, y) / hx;
+    const double firstV = lerp2(v, x, y) / hx;
+    const double midX = x - 0.5 * timestep * firstU;
+    const double midY = y - 0.5 * timestep * firstV;
+    const double midU = lerp2(u, midX, midY) / hx;
+    const double midV = lerp2(v, midX, midY) / hx;
+    const double lastX = x - 0.75 * timestep * midU;
+    const double lastY = y - 0.75 * timestep * midV;
+    const double lastU = lerp2(u, lastX, lastY);
+    const double lastV = lerp2(v, lastX, lastY);
+    x -= timestep * ((2.0 / 9.0) * firstU + (3.0 / 9.0) * midU + (4.0 / 9.0) * lastU);
+    y -= timestep * ((2.0 / 9.0) * firstV + (3.0 / 9.0) * midV + (4.0 / 9.0) * lastV);
+    // backProject
+    const int rx = imin(imax((int)(x - self.ox), 0), self.w - 1);
+    const int ry = imin(imax((int)(y - self.oy), 0), self.h - 1);
+    const size_t ri = rx + (size_t)ry * self.pitch;
+    if (cell[ri] != CELL_FLUID) {
+        x = (x - self.ox) * hx;
+        y = (y - self.oy) * hx;
+        body_closest_surface_point(bodies[body[ri]], x, y);
+        x = x / hx + self.ox;
+        y = y / hx + self.oy;
+    }
+    dst[ix + (size_t)iy * dst_pitch] = cerp2(self, x, y);
+}
+
 template <bool RK3_CERP>
 __global__ void __launch_bounds__(256) k_advect(double *__restrict__ dst, int dst_pitch, FieldView self, FieldView u,
                                                  FieldView v, double timestep, double hx) {
@@ -116,7 +156,10 @@ int launch_advect(ifl_ctx *c, int field, double timestep) {
     Field &f = c->fd[field];
     dim3 grid((f.w + 31) / 32, (f.h + 7) / 8);
     FieldView self = view(f), u = view(c->fd[IFL_FIELD_U]), v = view(c->fd[IFL_FIELD_V]);
-    if (c->version >= 2)
+    if (c->version >= 4)
+        k_advect_solid<<<grid, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, f.cell, f.body, u, v, timestep, c->hx,
+                                                    c->bodies_d);
+    else if (c->version >= 2)
         k_advect<true><<<grid, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, u, v, timestep, c->hx);
     else
         k_advect<false><<<grid, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, u, v, timestep, c->hx);

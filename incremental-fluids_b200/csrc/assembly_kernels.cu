@@ -102,13 +102,115 @@ __global__ void k_add_inflow(Arr src, int ix_lo, int ix_hi, int iy_lo, int iy_hi
     if (fabs(src.p[i]) < fabs(vi)) src.p[i] = vi;
 }
 
+// ---------------------------------------------------------- chapters 4+ variants ----
+__device__ __forceinline__ double bvx(const BodyDev &b, double y) { return (b.posY - y) * b.velTheta + b.velX; } // v4:125
+__device__ __forceinline__ double bvy(const BodyDev &b, double x) { return (x - b.posX) * b.velTheta + b.velY; } // v4:129
+
+// buildRhs with solid cells (v4:614-628) and, for chapter 5+, fractional volumes and the
+// solid-velocity blend terms (v5:654-683).
+__global__ void __launch_bounds__(256) k_build_rhs_solid(Arr r, Field d, Field u, Field v, double hx, double scale,
+                                                         const BodyDev *bodies, int nb, int curved) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int w = r.w, h = r.h;
+    if (x >= w || y >= h) return;
+    const size_t ic = x + (size_t)y * d.src.pitch;
+    const size_t iu = x + (size_t)y * u.src.pitch;
+    const size_t iv = x + (size_t)y * v.src.pitch;
+    double out = 0.0;
+    if (d.cell[ic] == CELL_FLUID) {
+        if (!curved) {
+            out = -scale * (u.src.p[iu + 1] - u.src.p[iu] + v.src.p[iv + v.src.pitch] - v.src.p[iv]);
+        } else {
+            const double uvr = u.volume.p[iu + 1], uvl = u.volume.p[iu];
+            const double vvb = v.volume.p[iv + v.src.pitch], vvt = v.volume.p[iv];
+            out = -scale * (uvr * u.src.p[iu + 1] - uvl * u.src.p[iu] + vvb * v.src.p[iv + v.src.pitch] - vvt * v.src.p[iv]);
+            const double vol = d.volume.p[ic];
+            if (nb > 0) {
+                if (x > 0) out -= (uvl - vol) * bvx(bodies[d.body[ic - 1]], (y + 0.5) * hx);
+                if (y > 0) out -= (vvt - vol) * bvy(bodies[d.body[ic - d.src.pitch]], (x + 0.5) * hx);
+                if (x < w - 1) out += (uvr - vol) * bvx(bodies[d.body[ic + 1]], (y + 0.5) * hx);
+                if (y < h - 1) out += (vvb - vol) * bvy(bodies[d.body[ic + d.src.pitch]], (x + 0.5) * hx);
+            }
+        }
+    }
+    r.p[x + (size_t)y * r.pitch] = out;
+}
+
+// buildPressureMatrix with solid cells, gather form of v5:694-712 (v4:652-670).  aDiag
+// receives its face factors in the raster order of the scattering cell: the face shared
+// with the cell above, with the cell to the left, then the cell's own right and lower
+// faces.  With fractional volumes the four factors differ, so the order is significant.
+__global__ void __launch_bounds__(256) k_build_matrix_solid(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, Field u, Field v,
+                                                            double scale, int curved) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int w = aDiag.w, h = aDiag.h;
+    if (x >= w || y >= h) return;
+    const int cp = d.src.pitch;
+    const size_t ic = x + (size_t)y * cp;
+    double diag = 0.0, ax = 0.0, ay = 0.0;
+    if (d.cell[ic] == CELL_FLUID) {
+        const size_t iu = x + (size_t)y * u.src.pitch;
+        const size_t iv = x + (size_t)y * v.src.pitch;
+        if (y > 0 && d.cell[ic - cp] == CELL_FLUID) diag += curved ? scale * v.volume.p[iv] : scale;
+        if (x > 0 && d.cell[ic - 1] == CELL_FLUID) diag += curved ? scale * u.volume.p[iu] : scale;
+        if (x < w - 1 && d.cell[ic + 1] == CELL_FLUID) {
+            const double factor = curved ? scale * u.volume.p[iu + 1] : scale;
+            diag += factor;
+            ax = -factor;
+        }
+        if (y < h - 1 && d.cell[ic + cp] == CELL_FLUID) {
+            const double factor = curved ? scale * v.volume.p[iv + v.src.pitch] : scale;
+            diag += factor;
+            ay = -factor;
+        }
+    }
+    const size_t i = x + (size_t)y * aDiag.pitch;
+    aDiag.p[i] = diag;
+    aPlusX.p[i] = ax;
+    aPlusY.p[i] = ay;
+}
+
+// applyPressure with solid cells (v4:796-810): only fluid cells push on their faces.
+__global__ void __launch_bounds__(256) k_apply_pressure_u_solid(Arr u, Arr p, Field d, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int W = p.w;
+    if (x > W || y >= u.h) return;
+    const size_t iu = x + (size_t)y * u.pitch;
+    const size_t ic = x + (size_t)y * d.src.pitch;
+    double val = u.p[iu];
+    if (x > 0 && d.cell[ic - 1] == CELL_FLUID) val += scale * p.p[x - 1 + (size_t)y * p.pitch];
+    if (x < W && d.cell[ic] == CELL_FLUID) val -= scale * p.p[x + (size_t)y * p.pitch];
+    u.p[iu] = val;
+}
+
+__global__ void __launch_bounds__(256) k_apply_pressure_v_solid(Arr v, Arr p, Field d, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int H = p.h;
+    if (x >= v.w || y > H) return;
+    const size_t iv = x + (size_t)y * v.pitch;
+    const size_t ic = x + (size_t)y * d.src.pitch;
+    double val = v.p[iv];
+    if (y > 0 && d.cell[ic - d.src.pitch] == CELL_FLUID) val += scale * p.p[x + (size_t)(y - 1) * p.pitch];
+    if (y < H && d.cell[ic] == CELL_FLUID) val -= scale * p.p[x + (size_t)y * p.pitch];
+    v.p[iv] = val;
+}
+
 static dim3 grid2d(int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); }
 
 int launch_build_rhs(ifl_ctx *c) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = 1.0 / c->hx;
-    k_build_rhs<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_U].src, c->fd[IFL_FIELD_V].src,
-                                                            scale);
+    if (c->version >= 4)
+        k_build_rhs_solid<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
+                                                                      c->fd[IFL_FIELD_V], c->hx, scale, c->bodies_d,
+                                                                      c->n_bodies, c->version >= 5);
+    else
+        k_build_rhs<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_U].src, c->fd[IFL_FIELD_V].src,
+                                                                scale);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -116,7 +218,12 @@ int launch_build_rhs(ifl_ctx *c) {
 int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = timestep / (density * c->hx * c->hx);
-    k_build_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
+    if (c->version >= 4)
+        k_build_matrix_solid<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
+                                                                         c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
+                                                                         c->fd[IFL_FIELD_V], scale, c->version >= 5);
+    else
+        k_build_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -125,6 +232,13 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = timestep / (density * c->hx);
     Field &u = c->fd[IFL_FIELD_U], &v = c->fd[IFL_FIELD_V];
+    if (c->version >= 4) {
+        k_apply_pressure_u_solid<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], scale);
+        IFL_LAUNCHED(c);
+        k_apply_pressure_v_solid<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], scale);
+        IFL_LAUNCHED(c);
+        return IFL_OK;
+    }
     k_apply_pressure_u<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, scale, 1);
     IFL_LAUNCHED(c);
     k_apply_pressure_v<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, scale, 1);

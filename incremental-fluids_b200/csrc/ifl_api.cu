@@ -3,6 +3,7 @@
 // Everything here is host code; all arithmetic happens in the kernels.
 #include "ifl_internal.cuh"
 
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,14 +64,53 @@ static void free_arr(Arr &a) {
     a.p = nullptr;
 }
 
-static int alloc_field(Field &f, int w, int h, double ox, double oy) {
+__global__ void k_fill2d(Arr a, double value) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < a.w && y < a.h) a.p[x + (size_t)y * a.pitch] = value;
+}
+
+static int fill_arr(const Arr &a, double value) {
+    k_fill2d<<<dim3((a.w + 255) / 256, a.h), 256>>>(a, value);
+    IFL_CUDA(cudaGetLastError());
+    return IFL_OK;
+}
+
+static int alloc_field(Field &f, int w, int h, double ox, double oy, bool solids) {
     f.w = w;
     f.h = h;
     f.ox = ox;
     f.oy = oy;
     int rc = alloc_arr(f.src, w, h);
     if (rc == IFL_OK) rc = alloc_arr(f.dst, w, h);
-    return rc;
+    if (rc != IFL_OK || !solids) return rc;
+    // FluidQuantity ctor of chapters 4+ (v5:356-377): every cell fluid, volume 1
+    if ((rc = alloc_arr(f.volume, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(f.normalX, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(f.normalY, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(f.phi, w + 1, h + 1)) != IFL_OK) return rc;
+    if ((rc = fill_arr(f.volume, 1.0)) != IFL_OK) return rc;
+    const size_t nb = (size_t)f.src.pitch * f.src.rows;
+    IFL_CUDA(cudaMalloc(&f.cell, nb));
+    IFL_CUDA(cudaMalloc(&f.body, nb));
+    IFL_CUDA(cudaMalloc(&f.mask, nb));
+    IFL_CUDA(cudaMemset(f.cell, 0, nb)); // CELL_FLUID
+    IFL_CUDA(cudaMemset(f.body, 0, nb));
+    IFL_CUDA(cudaMemset(f.mask, 0, nb));
+    IFL_CUDA(cudaMalloc(&f.solid_list, (size_t)w * h * sizeof(int)));
+    IFL_CUDA(cudaMalloc(&f.solid_count, sizeof(int)));
+    return IFL_OK;
+}
+
+static void free_field(Field &f) {
+    Arr *arrs[] = {&f.src, &f.dst, &f.volume, &f.normalX, &f.normalY, &f.phi};
+    for (int i = 0; i < 6; i++) free_arr(*arrs[i]);
+    if (f.cell) cudaFree(f.cell);
+    if (f.body) cudaFree(f.body);
+    if (f.mask) cudaFree(f.mask);
+    if (f.solid_list) cudaFree(f.solid_list);
+    if (f.solid_count) cudaFree(f.solid_count);
+    f.cell = f.body = f.mask = nullptr;
+    f.solid_list = f.solid_count = nullptr;
 }
 
 static Arr *buf_arr(ifl_ctx *c, int buf) {
@@ -123,8 +163,8 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
         return IFL_E_ARG;
     }
-    if (version > 3) {
-        set_error("ifl_create: chapter %d (solid bodies and later) is not available in this build", version);
+    if (version > 5) {
+        set_error("ifl_create: chapter %d (heat, variable density, FLIP) is not available in this build", version);
         return IFL_E_ARG;
     }
     int ndev = 0;
@@ -148,9 +188,21 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
             break;
         }
         // v3:404-406: d at cell centres, u/v on the staggered faces
-        if ((rc = alloc_field(c->fd[IFL_FIELD_D], w, h, 0.5, 0.5)) != IFL_OK) break;
-        if ((rc = alloc_field(c->fd[IFL_FIELD_U], w + 1, h, 0.0, 0.5)) != IFL_OK) break;
-        if ((rc = alloc_field(c->fd[IFL_FIELD_V], w, h + 1, 0.5, 0.0)) != IFL_OK) break;
+        const bool solids = version >= 4;
+        if ((rc = alloc_field(c->fd[IFL_FIELD_D], w, h, 0.5, 0.5, solids)) != IFL_OK) break;
+        if ((rc = alloc_field(c->fd[IFL_FIELD_U], w + 1, h, 0.0, 0.5, solids)) != IFL_OK) break;
+        if ((rc = alloc_field(c->fd[IFL_FIELD_V], w, h + 1, 0.5, 0.0, solids)) != IFL_OK) break;
+        if (solids) {
+            if ((rc = alloc_arr(c->pe, w, h)) != IFL_OK) break;
+            if ((rc = alloc_arr(c->fmask, w, h)) != IFL_OK) break;
+            if ((rc = fill_arr(c->fmask, 1.0)) != IFL_OK) break;
+            if (cudaMalloc(&c->bodies_d, MAX_BODIES * sizeof(BodyDev)) != cudaSuccess ||
+                cudaMalloc(&c->ext_ready, sizeof(int)) != cudaSuccess) {
+                set_error("ifl_create: body table allocation failed");
+                rc = IFL_E_CUDA;
+                break;
+            }
+        }
         Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
         const int ncells = pcg_chapter(c) ? 11 : 2; // chapters 1-2 only own _r and _p (v2:219-220)
         for (int i = 0; i < ncells && rc == IFL_OK; i++) rc = alloc_arr(*cells[i], w, h);
@@ -183,10 +235,11 @@ int ifl_destroy(ifl_ctx *c) {
     if (!c) return IFL_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 4; i++) {
-        free_arr(c->fd[i].src);
-        free_arr(c->fd[i].dst);
-    }
+    for (int i = 0; i < 4; i++) free_field(c->fd[i]);
+    free_arr(c->pe);
+    free_arr(c->fmask);
+    if (c->bodies_d) cudaFree(c->bodies_d);
+    if (c->ext_ready) cudaFree(c->ext_ready);
     Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
     for (int i = 0; i < 11; i++) free_arr(*cells[i]);
     if (c->partials) cudaFree(c->partials);
@@ -343,6 +396,132 @@ int ifl_flip(ifl_ctx *c, int field) {
     return IFL_OK;
 }
 
+// ---- chapters 4+: solid bodies ---------------------------------------------------------
+static int need_solids(ifl_ctx *c, const char *what) {
+    if (c->version < 4) {
+        set_error("%s: solid bodies belong to chapters 4+", what);
+        return IFL_E_ARG;
+    }
+    return IFL_OK;
+}
+
+int ifl_set_bodies(ifl_ctx *c, const ifl_body *bodies, int n) {
+    CHECK_CTX(c);
+    TRY(need_solids(c, "ifl_set_bodies"));
+    if (n < 0 || n > MAX_BODIES || (n > 0 && !bodies)) {
+        set_error("ifl_set_bodies: %d bodies (at most %d: FluidQuantity::_body is a uint8_t)", n, MAX_BODIES);
+        return IFL_E_ARG;
+    }
+    BodyDev tmp[MAX_BODIES];
+    for (int i = 0; i < n; i++) {
+        tmp[i].kind = bodies[i].kind;
+        tmp[i].pad = 0;
+        tmp[i].posX = bodies[i].pos_x;
+        tmp[i].posY = bodies[i].pos_y;
+        tmp[i].scaleX = bodies[i].scale_x;
+        tmp[i].scaleY = bodies[i].scale_y;
+        tmp[i].theta = bodies[i].theta;
+        tmp[i].velX = bodies[i].vel_x;
+        tmp[i].velY = bodies[i].vel_y;
+        tmp[i].velTheta = bodies[i].vel_theta;
+        tmp[i].cosT = cos(bodies[i].theta); // host libm, as rotate() does (v4:58-62)
+        tmp[i].sinT = sin(bodies[i].theta);
+    }
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    if (n > 0) IFL_CUDA(cudaMemcpy(c->bodies_d, tmp, n * sizeof(BodyDev), cudaMemcpyHostToDevice));
+    c->n_bodies = n;
+    return IFL_OK;
+}
+
+int ifl_fill_solid_fields(ifl_ctx *c, int field) {
+    CHECK_CTX(c);
+    TRY(need_solids(c, "ifl_fill_solid_fields"));
+    TRY(check_field(c, field));
+    return launch_fill_solid_fields(c, field);
+}
+
+int ifl_set_boundary_condition(ifl_ctx *c) {
+    CHECK_CTX(c);
+    TRY(need_solids(c, "ifl_set_boundary_condition"));
+    return launch_set_boundary_condition(c);
+}
+
+int ifl_extrapolate(ifl_ctx *c, int field) {
+    CHECK_CTX(c);
+    TRY(need_solids(c, "ifl_extrapolate"));
+    TRY(check_field(c, field));
+    return launch_extrapolate(c, field);
+}
+
+// aux arrays of a FluidQuantity: doubles (volume, normals, phi) or bytes (cell, body)
+static int aux_lookup(ifl_ctx *c, int field, int which, void **base, int *w, int *h, int *pitch, int *elsize) {
+    if (c->version < 4 || check_field(c, field) != IFL_OK) {
+        set_error("no solid-body arrays for field %d in chapter %d", field, c->version);
+        return IFL_E_ARG;
+    }
+    Field &f = c->fd[field];
+    const Arr *a = nullptr;
+    switch (which) {
+    case IFL_AUX_VOLUME: a = &f.volume; break;
+    case IFL_AUX_NORMAL_X: a = &f.normalX; break;
+    case IFL_AUX_NORMAL_Y: a = &f.normalY; break;
+    case IFL_AUX_PHI: a = &f.phi; break;
+    case IFL_AUX_CELL: *base = f.cell; break;
+    case IFL_AUX_BODY: *base = f.body; break;
+    default: set_error("bad aux id %d", which); return IFL_E_ARG;
+    }
+    if (a) {
+        *base = a->p;
+        *w = a->w;
+        *h = a->h;
+        *pitch = a->pitch;
+        *elsize = 8;
+    } else {
+        *w = f.w;
+        *h = f.h;
+        *pitch = f.src.pitch;
+        *elsize = 1;
+    }
+    return IFL_OK;
+}
+
+size_t ifl_aux_elems(const ifl_ctx *c, int field, int which) {
+    void *b;
+    int w, h, p, e;
+    if (!c || aux_lookup(const_cast<ifl_ctx *>(c), field, which, &b, &w, &h, &p, &e) != IFL_OK) return 0;
+    return (size_t)w * h;
+}
+
+int ifl_aux_download(ifl_ctx *c, int field, int which, void *host) {
+    CHECK_CTX(c);
+    void *b;
+    int w, h, p, e;
+    TRY(aux_lookup(c, field, which, &b, &w, &h, &p, &e));
+    IFL_CUDA(cudaMemcpy2DAsync(host, (size_t)w * e, b, (size_t)p * e, (size_t)w * e, h, cudaMemcpyDeviceToHost, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    return IFL_OK;
+}
+
+int ifl_aux_upload(ifl_ctx *c, int field, int which, const void *host) {
+    CHECK_CTX(c);
+    void *b;
+    int w, h, p, e;
+    TRY(aux_lookup(c, field, which, &b, &w, &h, &p, &e));
+    IFL_CUDA(cudaMemcpy2DAsync(b, (size_t)p * e, host, (size_t)w * e, (size_t)w * e, h, cudaMemcpyHostToDevice, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    if (field == IFL_FIELD_D && which == IFL_AUX_CELL) { // keep the factorisation's fluid mask in step
+        const uint8_t *cell = (const uint8_t *)host;
+        double *tmp = (double *)malloc((size_t)w * h * sizeof(double));
+        if (!tmp) return IFL_E_NOMEM;
+        for (size_t i = 0; i < (size_t)w * h; i++) tmp[i] = cell[i] == CELL_FLUID ? 1.0 : 0.0;
+        cudaError_t e2 = cudaMemcpy2D(c->fmask.p, (size_t)c->fmask.pitch * 8, tmp, (size_t)w * 8, (size_t)w * 8, h,
+                                      cudaMemcpyHostToDevice);
+        free(tmp);
+        IFL_CUDA(e2);
+    }
+    return IFL_OK;
+}
+
 // ---- FluidSolver private hot-path methods ----------------------------------------
 static int need_pcg(ifl_ctx *c, const char *what) {
     if (!pcg_chapter(c)) {
@@ -475,10 +654,28 @@ int ifl_add_inflow(ifl_ctx *c, double x, double y, double w, double h, double d,
     return IFL_OK;
 }
 
+// FluidSolver::update of chapters 4-5 (v5:927-953, v4:869-895)
+static int update_solids(ifl_ctx *c, double timestep, double density, ifl_solve_info *info) {
+    const int fields[3] = {IFL_FIELD_D, IFL_FIELD_U, IFL_FIELD_V};
+    for (int i = 0; i < 3; i++) TRY(launch_fill_solid_fields(c, fields[i]));
+    TRY(launch_set_boundary_condition(c));
+    TRY(launch_build_rhs(c));
+    TRY(launch_build_matrix(c, timestep, density));
+    TRY(launch_mic0_factor(c));
+    TRY(pcg_project(c, 2000, info));
+    TRY(launch_apply_pressure(c, timestep, density));
+    for (int i = 0; i < 3; i++) TRY(launch_extrapolate(c, fields[i]));
+    TRY(launch_set_boundary_condition(c));
+    for (int i = 0; i < 3; i++) TRY(launch_advect(c, fields[i], timestep));
+    for (int i = 0; i < 3; i++) TRY(ifl_flip(c, fields[i]));
+    return IFL_OK;
+}
+
 int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
     CHECK_CTX(c);
     ifl_solve_info local;
     ifl_solve_info *info = infos ? infos : &local;
+    if (c->version >= 4) return update_solids(c, timestep, density, info);
     TRY(launch_build_rhs(c));
     if (pcg_chapter(c)) { // v3:433-447
         TRY(launch_build_matrix(c, timestep, density));

@@ -30,11 +30,26 @@ struct Arr {
     __host__ __device__ size_t bytes() const { return (size_t)pitch * rows * sizeof(double); }
 };
 
-struct Field { // one FluidQuantity (v3:41-49)
+struct Field { // one FluidQuantity (v3:41-49; solid-body members v5:288-313)
     Arr src, dst;
     int w, h;
     double ox, oy;
+    // chapters 4+: solid fields, same pitch as src (phi is (w+1) x (h+1) with its own pitch)
+    Arr volume, normalX, normalY, phi;
+    uint8_t *cell, *body, *mask; // byte arrays, row pitch == src.pitch
+    int *solid_list;             // compacted indices (x + y*pitch) of interior non-fluid cells
+    int *solid_count;            // device counter for solid_list
 };
+
+// One SolidBody (v4:79-241) as plain data; sin/cos of theta are evaluated on the host
+// with libm so that rotate() (v4:58-62) is bit-identical to the reference.
+struct BodyDev {
+    int kind; // 0 SolidBox, 1 SolidSphere
+    int pad;
+    double posX, posY, scaleX, scaleY, theta, velX, velY, velTheta;
+    double cosT, sinT;
+};
+constexpr int MAX_BODIES = 256; // FluidQuantity::_body is uint8_t (v4:253)
 
 // Device-resident scalars of one PCG / Gauss-Seidel solve (no host round trips
 // inside the loop; the host only reads `done`/`iter` through a pinned mirror).
@@ -59,6 +74,11 @@ struct ifl_ctx {
     cudaStream_t stream;
     ifl::Field fd[4]; // d, u, v, t
     ifl::Arr r, p, z, s, q, precon, aDiag, aPlusX, aPlusY, cx, cy;
+    ifl::Arr pe;    // chapters 4+: precon with +0.0 at non-fluid cells (what the masked sweeps multiply by)
+    ifl::Arr fmask; // chapters 4+: 1.0 at fluid cells of _d, 0.0 elsewhere (operand of the masked factorisation)
+    ifl::BodyDev *bodies_d; // [MAX_BODIES]
+    int n_bodies;
+    int *ext_ready;         // extrapolate(): device counter of cells resolved in the last batch of rounds
     double *partials;          // [MAX_PARTIALS] block partials (sum or max)
     int n_partials;            // valid entries written by the last reducing kernel
     ifl::SolveScalars *scal;   // device
@@ -125,6 +145,7 @@ __host__ __device__ __forceinline__ double std_min(double a, double b) { return 
 __host__ __device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
 __host__ __device__ __forceinline__ int imin(int a, int b) { return (b < a) ? b : a; }
 __host__ __device__ __forceinline__ int imax(int a, int b) { return (a < b) ? b : a; }
+enum { CELL_FLUID = 0, CELL_SOLID = 1 }; // v4:70-73
 
 // ------------------------------------------------- deterministic block reductions --
 // Fixed-shape trees (xor-shuffle inside the warp, then a fixed loop over warps), so a
@@ -173,6 +194,10 @@ int launch_mic0_factor(ifl_ctx *c);
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
+// solid_kernels.cu (chapters 4+)
+int launch_fill_solid_fields(ifl_ctx *c, int field);
+int launch_set_boundary_condition(ifl_ctx *c);
+int launch_extrapolate(ifl_ctx *c, int field);
 // assembly_kernels.cu
 int launch_build_rhs(ifl_ctx *c);
 int launch_build_matrix(ifl_ctx *c, double timestep, double density);

@@ -49,7 +49,7 @@
 
 namespace ifl {
 
-enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3 };
+enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3, KIND_FACTOR_M = 4 }; // _M: with solid cells (v5:715-744)
 
 // A tile is one TMA box: 33 rows x 32 doubles, dense (256-byte rows).  Forward kinds
 // fetch memory rows y0-1 .. y0+31 (tile row 0 = the upstream strip's last row, lane t
@@ -60,7 +60,7 @@ constexpr int TP = 32;
 constexpr int TROWS = 33;
 constexpr int TILE_DOUBLES = TROWS * TP;     // 1056
 constexpr int TILE_BYTES = TILE_DOUBLES * 8; // 8448 (multiple of 128)
-constexpr int MAX_TILES = 6;
+constexpr int MAX_TILES = 7;
 constexpr int MAX_STAGES = 8;
 constexpr int HG = 8; // hand-off granularity in columns (publisher and consumer side)
 constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
@@ -71,6 +71,7 @@ struct TileDesc {
     int load;      // fetched HBM -> smem by TMA
     int row_shift; // fetch memory rows shifted by this many rows (Gauss-Seidel: the row below)
     int store;     // drained smem -> HBM
+    double *p2;    // optional second store target, written only where the value is non-zero
 };
 
 struct SweepParams {
@@ -87,6 +88,7 @@ struct SweepParams {
     int gated;        // skip when scal->done
     double *partials; // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
     double scale;     // KIND_GS: timestep/(density*hx*hx)  v2:234
+    int mask_tile;    // >= 0: results are stored only where this tile is non-zero (fluid cells), else -1
     unsigned long long *times; // diagnostics: [nby][2] globaltimer ns at strip start / end (or null)
 };
 
@@ -228,7 +230,7 @@ struct Carry {
 
 // Operands of one cell, fetched one step ahead of their use.
 struct Ops {
-    double a, b, c, d, e, halo;
+    double a, b, c, d, e, f, halo;
 };
 
 // p -> tile 0, this lane's row, this step's column (shared-space byte address); tile k
@@ -259,6 +261,7 @@ __device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint
         o.c = lds_f64(p + 2 * TILE_BYTES);      // aPlusY own
         o.d = lds_f64(p + 1 * TILE_BYTES + UP); // aPlusX upper
         o.e = lds_f64(p + 2 * TILE_BYTES + UP); // aPlusY upper
+        if (KIND == KIND_FACTOR_M) o.f = lds_f64(p + 6 * TILE_BYTES); // 1.0 at fluid cells, else 0.0
     }
     o.halo = lds_f64(ph); // same address in every lane (broadcast); only lane 0 uses it
 }
@@ -311,7 +314,14 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         e = e - (pyu * pyu + tau * pxu * pyu);           // v3:263
         if (e < sigma * o.a) e = o.a;                    // v3:266-267
         znew = 1.0 / sqrt(e);                            // v3:269
-        const double cxo = o.b * znew, cyo = o.c * znew;
+        double cxo = o.b * znew, cyo = o.c * znew;
+        if (KIND == KIND_FACTOR_M && o.f == 0.0) {
+            // non-fluid cell (v5:722-723 `continue`): the reference skips every term that
+            // involves it; feeding +0.0 downstream makes those terms exact no-ops
+            znew = 0.0;
+            cxo = 0.0;
+            cyo = 0.0;
+        }
         sts_f64(p + 3 * TILE_BYTES, znew);
         sts_f64(p + 4 * TILE_BYTES, cxo);
         sts_f64(p + 5 * TILE_BYTES, cyo);
@@ -428,7 +438,7 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.ncols = P.nbx * 32;
     }
     Ops ops;
-    ops.a = ops.b = ops.c = ops.d = ops.e = ops.halo = 0.0;
+    ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
     mbar_wait(&full[0], 0, dead, P.scal);
     if (has_up) wait_counter(halo_cols_addr, HG, dead, P.scal);
@@ -604,10 +614,22 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
                 }
                 if (y < P.H) {
                     double *dst = g + x + (size_t)y * P.pitch;
-                    if (x + 1 < P.W)
-                        *reinterpret_cast<double2 *>(dst) = v;
-                    else if (x < P.W)
-                        dst[0] = v.x;
+                    if (P.mask_tile < 0) {
+                        if (x + 1 < P.W)
+                            *reinterpret_cast<double2 *>(dst) = v;
+                        else if (x < P.W)
+                            dst[0] = v.x;
+                    } else { // chapters 4+: non-fluid cells keep their old value (v5:751-752)
+                        const double2 mk =
+                            *reinterpret_cast<const double2 *>(stage + P.mask_tile * TILE_DOUBLES + trow * TP + l16 * 2);
+                        if (x < P.W && mk.x != 0.0) dst[0] = v.x;
+                        if (x + 1 < P.W && mk.y != 0.0) dst[1] = v.y;
+                    }
+                    if (P.t[k].p2) { // e.g. precon itself: written at fluid cells only (v5:741)
+                        double *d2 = P.t[k].p2 + x + (size_t)y * P.pitch;
+                        if (x < P.W && v.x != 0.0) d2[0] = v.x;
+                        if (x + 1 < P.W && v.y != 0.0) d2[1] = v.y;
+                    }
                 }
             }
         }
@@ -632,7 +654,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, uint64_t *don
     const int nst = P.nst;
     const int stage_doubles = P.nt * TILE_DOUBLES;
     const int ncols = P.nbx * 32;
-    int swept = (KIND == KIND_FWD) ? 4 : (KIND == KIND_FACTOR ? 3 : 0);
+    int swept = (KIND == KIND_FWD) ? 4 : ((KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? 3 : 0);
     const double *last_row = smem + swept * TILE_DOUBLES + G::lane_row(31) * TP; // tile row of the strip's last row
     uint4 *out = P.handoff + (size_t)sj * ncols;
     const uint32_t progress_addr = smem_u32(&counters[0]);
@@ -817,6 +839,7 @@ void sweep_free(ifl_ctx *c) {
 struct TileSpec {
     const Arr *a;
     int load, row_shift, store;
+    const Arr *a2; // optional second store target (non-zero values only)
 };
 
 template <int KIND, bool DOT>
@@ -828,6 +851,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         P.t[k].load = spec[k].load;
         P.t[k].row_shift = spec[k].row_shift;
         P.t[k].store = spec[k].store;
+        P.t[k].p2 = spec[k].a2 ? spec[k].a2->p : nullptr;
         if (spec[k].load) {
             int rc = get_map(c, *spec[k].a, &P.map[k]);
             if (rc != IFL_OK) return rc;
@@ -851,12 +875,12 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     P.scal = c->scal;
     P.times = c->sweep_times;
     const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)nst * 32 * sizeof(double);
-    static bool attr_set[4][2] = {{false, false}, {false, false}, {false, false}, {false, false}};
+    static bool attr_set[5][2] = {{false, false}, {false, false}, {false, false}, {false, false}, {false, false}};
     if (!attr_set[KIND][DOT]) {
         IFL_CUDA(cudaFuncSetAttribute(k_sweep<KIND, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr_set[KIND][DOT] = true;
     }
-    ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : KIND == KIND_FACTOR ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
+    ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
     k_sweep<KIND, DOT><<<P.nby, 160, smem, c->stream>>>(P);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -865,16 +889,32 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
 int launch_mic0_factor(ifl_ctx *c) {
     SweepParams P;
     memset(&P, 0, sizeof P);
-    const TileSpec spec[6] = {{&c->aDiag, 1, 0, 0}, {&c->aPlusX, 1, 0, 0}, {&c->aPlusY, 1, 0, 0},
-                              {&c->precon, 0, 0, 1}, {&c->cx, 0, 0, 1},    {&c->cy, 0, 0, 1}};
+    P.mask_tile = -1;
+    if (c->version >= 4) {
+        // precon keeps its old value at non-fluid cells; pe is the +0.0-masked copy the solves use
+        const TileSpec spec[7] = {{&c->aDiag, 1, 0, 0, nullptr}, {&c->aPlusX, 1, 0, 0, nullptr}, {&c->aPlusY, 1, 0, 0, nullptr},
+                                  {&c->pe, 0, 0, 1, &c->precon}, {&c->cx, 0, 0, 1, nullptr},    {&c->cy, 0, 0, 1, nullptr},
+                                  {&c->fmask, 1, 0, 0, nullptr}};
+        return launch_sweep<KIND_FACTOR_M, false>(c, P, spec, 7, 3);
+    }
+    const TileSpec spec[6] = {{&c->aDiag, 1, 0, 0, nullptr}, {&c->aPlusX, 1, 0, 0, nullptr}, {&c->aPlusY, 1, 0, 0, nullptr},
+                              {&c->precon, 0, 0, 1, nullptr}, {&c->cx, 0, 0, 1, nullptr},    {&c->cy, 0, 0, 1, nullptr}};
     return launch_sweep<KIND_FACTOR, false>(c, P, spec, 6, 4);
 }
+
+// chapters 4+ multiply by `pe` (precon with +0.0 at non-fluid cells) and store only fluid cells
+static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
-    const TileSpec spec[5] = {{&a, 1, 0, 0}, {&c->cx, 1, 0, 0}, {&c->cy, 1, 0, 0}, {&c->precon, 1, 0, 0}, {&dst, 0, 0, 1}};
+    P.mask_tile = c->version >= 4 ? 3 : -1;
+    const TileSpec spec[5] = {{&a, 1, 0, 0, nullptr},
+                              {&c->cx, 1, 0, 0, nullptr},
+                              {&c->cy, 1, 0, 0, nullptr},
+                              {&precon_operand(c), 1, 0, 0, nullptr},
+                              {&dst, 0, 0, 1, nullptr}};
     return launch_sweep<KIND_FWD, false>(c, P, spec, 5, 5);
 }
 
@@ -882,7 +922,12 @@ int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, boo
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
-    const TileSpec spec[5] = {{&dst, 1, 0, 1}, {&c->cx, 1, 0, 0}, {&c->cy, 1, 0, 0}, {&c->precon, 1, 0, 0}, {&r_for_dot, 1, 0, 0}};
+    P.mask_tile = c->version >= 4 ? 3 : -1;
+    const TileSpec spec[5] = {{&dst, 1, 0, 1, nullptr},
+                              {&c->cx, 1, 0, 0, nullptr},
+                              {&c->cy, 1, 0, 0, nullptr},
+                              {&precon_operand(c), 1, 0, 0, nullptr},
+                              {&r_for_dot, 1, 0, 0, nullptr}};
     if (with_dot) {
         P.partials = c->partials;
         c->n_partials = (c->H + 31) / 32;
@@ -913,8 +958,9 @@ static int enqueue_gs_sweep(ifl_ctx *c, double scale) {
     memset(&P, 0, sizeof P);
     P.gated = 1;
     P.scale = scale;
+    P.mask_tile = -1;
     // tile 1 is p again, fetched one row further down: the old values of the row below (v2:264)
-    const TileSpec spec[3] = {{&c->p, 1, 0, 1}, {&c->p, 1, 1, 0}, {&c->r, 1, 0, 0}};
+    const TileSpec spec[3] = {{&c->p, 1, 0, 1, nullptr}, {&c->p, 1, 1, 0, nullptr}, {&c->r, 1, 0, 0, nullptr}};
     P.partials = c->partials;
     c->n_partials = (c->H + 31) / 32;
     int rc = launch_sweep<KIND_GS, false>(c, P, spec, 3, 5);
