@@ -1,0 +1,45 @@
+// plume_main.cpp -- the reference's main() (3-conjugate-gradients/Fluid.cpp:468-499,
+// 5-curved-boundaries/Fluid.cpp:975-1016) written against the drop-in header; instead of
+// PNG frames it prints an FNV-1a-64 of the RGBA image every frame.  Usage:
+//     plume_v<N> [size=128] [frames=5]
+#include <stdint.h>
+#include <string.h>
+
+#include "FluidSolver.hpp"
+
+int main(int argc, char **argv) {
+    const int size = argc > 1 ? atoi(argv[1]) : 128;
+    const int frames = argc > 2 ? atoi(argv[2]) : 5;
+    const double density = 0.1, timestep = 0.005;
+    unsigned char *image = new unsigned char[(size_t)size * size * 4];
+#if IFL_CHAPTER >= 4
+    std::vector<SolidBody *> bodies;
+    bodies.push_back(new SolidBox(0.5, 0.6, 0.7, 0.1, M_PI * 0.25, 0.0, 0.0, 0.0)); // v5:986
+    std::vector<const SolidBody *> cBodies;
+    for (unsigned i = 0; i < bodies.size(); i++) cBodies.push_back(bodies[i]);
+    FluidSolver *solver = new FluidSolver(size, size, density, cBodies);
+#else
+    FluidSolver *solver = new FluidSolver(size, size, density);
+#endif
+    for (int f = 0; f < frames; f++) {
+        for (int i = 0; i < 4; i++) {
+#if IFL_CHAPTER == 1
+            solver->addInflow(0.45, 0.2, 0.1, 0.01, 1.0, 0.0, 3.0); // v1:362
+#else
+            solver->addInflow(0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0); // v3:485
+#endif
+            solver->update(timestep);
+            fflush(stdout);
+        }
+        solver->toImage(image);
+        uint64_t hsh = 0xcbf29ce484222325ULL;
+        for (size_t i = 0; i < (size_t)size * size * 4; i++) hsh = (hsh ^ image[i]) * 0x100000001b3ULL;
+        printf("Frame%05d fnv64(rgba)=%016llx\n", f, (unsigned long long)hsh);
+#if IFL_CHAPTER >= 4
+        for (unsigned i = 0; i < bodies.size(); i++) bodies[i]->update(timestep);
+#endif
+    }
+    delete solver;
+    delete[] image;
+    return 0;
+}
