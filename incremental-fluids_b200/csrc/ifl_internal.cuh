@@ -89,7 +89,9 @@ struct ifl_ctx {
     unsigned long long *ticket;  // strip ticket counter
     unsigned long long epoch;    // last used handoff epoch
     int n_strips;
-    unsigned long long sweep_launches; // sweeps launched so far (ticket base = launches * strips)
+    unsigned long long sweep_launches; // sweeps launched so far
+    unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
+    int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     void *map_cache;                   // TMA tensor maps keyed by array base pointer
     unsigned long long *sweep_times_buf; // [strips][2] diagnostics buffer
     unsigned long long *sweep_times;     // == sweep_times_buf while ifl_debug_sweep_times is armed, else null

@@ -45,6 +45,7 @@
 #include "ifl_internal.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace ifl {
@@ -63,6 +64,7 @@ constexpr int TILE_BYTES = TILE_DOUBLES * 8; // 8448 (multiple of 128)
 constexpr int MAX_TILES = 7;
 constexpr int MAX_STAGES = 8;
 constexpr int HG = 8; // hand-off granularity in columns (publisher and consumer side)
+constexpr int HR = 16; // hand-off ring depth in blocks (512 columns): deep enough that back-pressure never binds
 constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
 constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
 
@@ -89,6 +91,7 @@ struct SweepParams {
     double *partials; // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
     double scale;     // KIND_GS: timestep/(density*hx*hx)  v2:234
     int mask_tile;    // >= 0: results are stored only where this tile is non-zero (fluid cells), else -1
+    int cs;           // thread-block cluster size (1 = no cluster): strips of one cluster hand off through DSMEM
     unsigned long long *times; // diagnostics: [nby][2] globaltimer ns at strip start / end (or null)
 };
 
@@ -143,6 +146,38 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// ---- thread-block cluster / distributed shared memory
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address of THIS CTA's layout) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, unsigned rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_remote_f64(uint32_t raddr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_remote_u32_release(uint32_t raddr, unsigned v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_remote_u32(uint32_t raddr) {
+    unsigned v;
+    asm volatile("ld.relaxed.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(raddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32_acquire(uint32_t a) { // pairs with st_remote_u32_release
+    unsigned v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
 // NCCL-LL style message: {lo, epoch, hi, epoch} in one 16-byte store / load.
 __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch) {
     const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
@@ -178,6 +213,22 @@ __device__ __forceinline__ void lds_f64_if(double &v, uint32_t a, bool pred) {
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
+// store only if `pred` (EDGE macro-steps: lanes outside the strip run the same code, unbranched)
+template <bool ALWAYS>
+__device__ __forceinline__ void sts_f64_p(uint32_t a, double v, bool pred) {
+    if (ALWAYS) {
+        sts_f64(a, v);
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.u32 p, %2, 0;\n\t"
+            "@p st.shared.f64 [%0], %1;\n\t"
+            "}" ::"r"(a),
+            "d"(v), "r"((unsigned)pred)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void sts_u32_volatile(uint32_t a, unsigned v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -188,9 +239,9 @@ __device__ __forceinline__ unsigned lds_u32_volatile(uint32_t a) {
 }
 // Bounded spin until the shared counter at `a` reaches `need`.
 __device__ __forceinline__ void wait_counter(uint32_t a, unsigned need, volatile int *dead, SolveScalars *scal) {
-    if (lds_u32_volatile(a) >= need) return;
+    if (lds_u32_acquire(a) >= need) return;
     unsigned n = 0;
-    while (lds_u32_volatile(a) < need) {
+    while (lds_u32_acquire(a) < need) {
         if (++n > WATCHDOG_POLLS || *dead) {
             *dead = 1;
             scal->watchdog = 1;
@@ -278,9 +329,11 @@ struct GsConst {
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
 // logical column.  Returns the new value of the swept variable; writes results into the tile.
-template <int KIND, bool DOT>
-__device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint32_t p, int c, const GsConst &gs) {
+template <int KIND, bool DOT, bool ALWAYS>
+__device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint32_t p, int c, const GsConst &gs,
+                                       bool active) {
     double znew;
+    const Carry old = cr;
     if (KIND == KIND_GS) {
         // Missing neighbours read +0.0 (left: initial carry, up: zeroed halo row, right:
         // predicated in fetch, down: zero pad row), and `off - scale*(+0.0)` is an exact
@@ -294,18 +347,18 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         const double diag = cnt == 4 ? gs.d4 : (cnt == 3 ? gs.d3 : (cnt == 2 ? gs.d2 : gs.d1));
         znew = (o.d - off) / diag;       // v2:267
         if (gs.yvalid && c < gs.W) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
-        sts_f64(p, znew);                // v2:271
+        sts_f64_p<ALWAYS>(p, znew, active); // v2:271
     } else if (KIND == KIND_FWD) {
         double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
         t = t - o.c * up;                  // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
         znew = t * o.d;                    // v3:285
-        sts_f64(p + 4 * TILE_BYTES, znew);
+        sts_f64_p<ALWAYS>(p + 4 * TILE_BYTES, znew, active);
         cr.c1 = o.b;
     } else if (KIND == KIND_BWD) {
         double t = o.a - o.b * cr.zprev; // v3:297  t -= aPlusX[idx]*precon[idx]*dst[idx+1]
         t = t - o.c * up;                // v3:299  t -= aPlusY[idx]*precon[idx]*dst[idx+w]
         znew = t * o.d;                  // v3:301
-        sts_f64(p, znew);                // (z.r of v3:374 is accumulated by the storer warp)
+        sts_f64_p<ALWAYS>(p, znew, active); // (z.r of v3:374 is accumulated by the storer warp)
     } else {
         const double tau = 0.97, sigma = 0.25; // v3:248-249
         double e = o.a;
@@ -322,13 +375,19 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
             cxo = 0.0;
             cyo = 0.0;
         }
-        sts_f64(p + 3 * TILE_BYTES, znew);
-        sts_f64(p + 4 * TILE_BYTES, cxo);
-        sts_f64(p + 5 * TILE_BYTES, cyo);
+        sts_f64_p<ALWAYS>(p + 3 * TILE_BYTES, znew, active);
+        sts_f64_p<ALWAYS>(p + 4 * TILE_BYTES, cxo, active);
+        sts_f64_p<ALWAYS>(p + 5 * TILE_BYTES, cyo, active);
         cr.c1 = cxo;
         cr.c2 = cyo;
     }
     cr.zprev = znew;
+    if (!ALWAYS) { // lanes outside the strip keep their (zero) state
+        cr.zprev = sel_f64(active, cr.zprev, old.zprev);
+        cr.c1 = sel_f64(active, cr.c1, old.c1);
+        cr.c2 = sel_f64(active, cr.c2, old.c2);
+        cr.acc = sel_f64(active, cr.acc, old.acc);
+    }
     return znew;
 }
 
@@ -393,9 +452,7 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         const int d0 = kk - lane;
         const bool active = (EDGE == 0) ? true : (EDGE == 1 ? d0 >= 0 : d0 < 0);
         up = sel_f64(lane == 0, ops.halo, up);
-        if (active) {
-            cell<KIND, DOT>(ops, cr, up, p, 32 * m + d0, gs);
-        }
+        cell<KIND, DOT, EDGE == 0>(ops, cr, up, p, 32 * m + d0, gs, active);
         // the strip's last row (lane 31) has just completed another group of HG columns
         if (((kk + 2) % HG) == 0) {
             sts_u32_volatile(progress_addr, (unsigned)imax(32 * m + kk - 30, 0));
@@ -458,8 +515,8 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         const uint32_t s_prev = row0 + sp * stage_bytes;
         const uint32_t s_cur = row0 + sc * stage_bytes;
         const uint32_t s_next = row0 + sn * stage_bytes;
-        const uint32_t h_cur = halo0 + sc * 256u;
-        const uint32_t h_next = halo0 + (has_next ? sn : sc) * 256u;
+        const uint32_t h_cur = halo0 + (uint32_t)(m % HR) * 256u;
+        const uint32_t h_next = halo0 + (uint32_t)((has_next ? m + 1 : m) % HR) * 256u;
         const uint32_t skew = (uint32_t)(DIR * lane), blk = (uint32_t)(DIR * 32);
         LaneBases lb;
         if (m == 0) { // no block m-1: idle lanes alias block 0
@@ -544,8 +601,8 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
     const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
     unsigned polls = 0;
     for (int m = 0; m < nbx; m++) {
-        const int st = m % nst;
-        if (m >= nst) wait_counter(progress_addr, (unsigned)(32 * (m - nst + 1)), dead, P.scal);
+        const int st = m % HR;
+        if (m >= HR) wait_counter(progress_addr, (unsigned)(32 * (m - HR + 1)), dead, P.scal);
         const uint4 *src = up_row + (size_t)m * 32 + lane;
         bool have = false;
         unsigned published = 0; // columns of this block already released
@@ -580,7 +637,12 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
 // Drains finished result tiles and, for the backward solve of the PCG loop, folds in
 // dotProduct(z, r) (v3:374): each lane accumulates its cells in a fixed order, the warp
 // sum goes to partials[strip].  Pad cells hold exact zeros and do not perturb the sum.
-template <int KIND, bool DOT>
+// MASKED (chapters 4+): a result is stored only where tile 3 (pe) is non-zero, i.e. at
+// fluid cells; non-fluid cells keep their old value (v5:751-752).  The masked
+// factorisation additionally writes precon itself where the value is non-zero (v5:741).
+// All loads of a tile are issued before its stores so that the drain takes a few hundred
+// cycles per block and never throttles the compute warp.
+template <int KIND, bool DOT, bool MASKED>
 __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, uint64_t *empty, int sj, int lane,
                             volatile int *dead) {
     typedef Geo<KIND> G;
@@ -589,46 +651,62 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
     const int ty = G::BWD ? (P.nby - 1 - sj) : sj;
     const int y0 = ty * 32;
     const int half = lane >> 4, l16 = lane & 15;
+    const int toff = (G::BWD ? half : 1 + half) * TP + l16 * 2; // this lane's first element inside a tile
     double acc = 0.0;
     for (int m = 0; m < P.nbx; m++) {
         const int st = m % nst;
-        double *stage = smem + st * stage_doubles;
+        const double *stage = smem + st * stage_doubles;
         mbar_wait(&done[st], (m / nst) & 1, dead, P.scal);
         const int tx = G::BWD ? (P.nbx - 1 - m) : m;
         const int x = tx * 32 + l16 * 2;
+        const bool x0 = x < P.W, x1 = x + 1 < P.W;
         for (int k = 0; k < P.nt; k++) {
             if (!P.t[k].store) continue;
-            const double *tile = stage + k * TILE_DOUBLES;
-            const double *rtile = stage + 4 * TILE_DOUBLES; // KIND_BWD with dot: tile 4 holds r
-            double *g = P.t[k].p;
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {
-                const int ry = i * 2 + half; // row inside the strip, memory order
-                const int trow = G::BWD ? ry : 1 + ry;
-                const int y = y0 + ry;
-                const double2 v = *reinterpret_cast<const double2 *>(tile + trow * TP + l16 * 2);
-                if (DOT && k == 0) {
-                    const double2 rv = *reinterpret_cast<const double2 *>(rtile + trow * TP + l16 * 2);
-                    acc += v.x * rv.x;
-                    acc += v.y * rv.y;
+            const double *tile = stage + k * TILE_DOUBLES + toff;
+            double2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = *reinterpret_cast<const double2 *>(tile + i * 2 * TP);
+            if (DOT && k == 0) { // KIND_BWD with dot: tile 4 holds r
+                const double *rt = stage + 4 * TILE_DOUBLES + toff;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const double2 rv = *reinterpret_cast<const double2 *>(rt + i * 2 * TP);
+                    acc += v[i].x * rv.x;
+                    acc += v[i].y * rv.y;
                 }
-                if (y < P.H) {
-                    double *dst = g + x + (size_t)y * P.pitch;
-                    if (P.mask_tile < 0) {
-                        if (x + 1 < P.W)
-                            *reinterpret_cast<double2 *>(dst) = v;
-                        else if (x < P.W)
-                            dst[0] = v.x;
-                    } else { // chapters 4+: non-fluid cells keep their old value (v5:751-752)
-                        const double2 mk =
-                            *reinterpret_cast<const double2 *>(stage + P.mask_tile * TILE_DOUBLES + trow * TP + l16 * 2);
-                        if (x < P.W && mk.x != 0.0) dst[0] = v.x;
-                        if (x + 1 < P.W && mk.y != 0.0) dst[1] = v.y;
+            }
+            double *g = P.t[k].p + x + (size_t)(y0 + half) * P.pitch;
+            if (!MASKED || KIND == KIND_FACTOR_M) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    double *dst = g + (size_t)(i * 2) * P.pitch;
+                    if (y0 + half + i * 2 < P.H) {
+                        if (x1)
+                            *reinterpret_cast<double2 *>(dst) = v[i];
+                        else if (x0)
+                            dst[0] = v[i].x;
                     }
-                    if (P.t[k].p2) { // e.g. precon itself: written at fluid cells only (v5:741)
-                        double *d2 = P.t[k].p2 + x + (size_t)y * P.pitch;
-                        if (x < P.W && v.x != 0.0) d2[0] = v.x;
-                        if (x + 1 < P.W && v.y != 0.0) d2[1] = v.y;
+                }
+                if (KIND == KIND_FACTOR_M && P.t[k].p2) { // precon: fluid cells only
+                    double *g2 = P.t[k].p2 + x + (size_t)(y0 + half) * P.pitch;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        double *dst = g2 + (size_t)(i * 2) * P.pitch;
+                        if (y0 + half + i * 2 < P.H) {
+                            if (x0 && v[i].x != 0.0) dst[0] = v[i].x;
+                            if (x1 && v[i].y != 0.0) dst[1] = v[i].y;
+                        }
+                    }
+                }
+            } else {
+                const double *mt = stage + 3 * TILE_DOUBLES + toff; // pe: non-zero at fluid cells
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const double2 mk = *reinterpret_cast<const double2 *>(mt + i * 2 * TP);
+                    double *dst = g + (size_t)(i * 2) * P.pitch;
+                    if (y0 + half + i * 2 < P.H) {
+                        if (x0 && mk.x != 0.0) dst[0] = v[i].x;
+                        if (x1 && mk.y != 0.0) dst[1] = v[i].y;
                     }
                 }
             }
@@ -644,12 +722,17 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
 }
 
 // -------------------------------------------------------------- publisher warp ----
-// Forwards the strip's last row to the downstream strip as LL messages, HG columns at a
-// time, as soon as the compute warp's progress counter says they are final.  It holds
-// each stage until its 32 columns have been sent (second arrival on done[]).
+// Forwards the strip's last row to the downstream strip, HG columns at a time, as soon as
+// the compute warp's progress counter says they are final.
+//   * downstream strip in the same thread-block cluster: the values are stored straight
+//     into that CTA's hand-off ring (distributed shared memory) and its hand-off counter is
+//     bumped with a release store -- ~a few hundred cycles end to end, nothing goes through L2;
+//   * otherwise: NCCL-LL style 16-byte messages {lo, epoch, hi, epoch} through L2, picked up
+//     by the downstream CTA's poller warp.
+// It holds each stage until its 32 columns have been sent (second arrival on done[]).
 template <int KIND>
-__device__ void publisher_warp(const SweepParams &P, double *smem, uint64_t *done, int sj, int lane,
-                               volatile int *dead, unsigned *counters) {
+__device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_s, uint64_t *done, int sj, int lane,
+                               volatile int *dead, unsigned *counters, unsigned rank) {
     typedef Geo<KIND> G;
     const int nst = P.nst;
     const int stage_doubles = P.nt * TILE_DOUBLES;
@@ -658,26 +741,47 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, uint64_t *don
     const double *last_row = smem + swept * TILE_DOUBLES + G::lane_row(31) * TP; // tile row of the strip's last row
     uint4 *out = P.handoff + (size_t)sj * ncols;
     const uint32_t progress_addr = smem_u32(&counters[0]);
-    // The common case is one group of HG columns per round, inside one block: lanes
-    // 0..HG-1 each forward one value.  Block / stage bookkeeping is incremental (no
-    // divisions in the loop).
+    const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs;
+    // downstream CTA's hand-off ring, hand-off counter and progress counter (same layout as ours)
+    const uint32_t r_halo = dsmem ? mapa(smem_u32(halo_s), rank + 1) : 0;
+    const uint32_t r_halo_cols = dsmem ? mapa(smem_u32(&counters[1]), rank + 1) : 0;
+    const uint32_t r_progress = dsmem ? mapa(smem_u32(&counters[0]), rank + 1) : 0;
+    int down_progress = 0; // last value read from the downstream strip's own progress counter
     int sent = 0;        // columns forwarded so far
-    int blk_end = 32;    // first column of the next block
-    int st = 0;          // stage of the block `sent` lies in
-    const double *row = last_row; // last row of that stage's swept tile
+    int blk = 0;         // block `sent` lies in
+    int st = 0;          // its stage
+    const double *row = last_row;
     unsigned n = 0;
     while (sent < ncols) {
         const int prog = (int)lds_u32_volatile(progress_addr);
         if (prog > sent) {
             while (sent < prog) {
+                const int blk_end = (blk + 1) * 32;
                 const int upto = prog < blk_end ? prog : blk_end; // stay inside one block
                 const int c = sent + lane;
-                if (c < upto) ll_store(out + c, row[G::tcol(c & 31)], P.epoch);
+                if (dsmem) {
+                    // the ring slot of block `blk` is free once the downstream strip's last row has
+                    // left block blk - HR (its lane 0 is further ahead still)
+                    while (blk >= HR && down_progress < 32 * (blk - HR + 1)) {
+                        down_progress = (int)ld_remote_u32(r_progress);
+                        if (++n > WATCHDOG_POLLS || *dead) {
+                            *dead = 1;
+                            P.scal->watchdog = 1;
+                            break;
+                        }
+                    }
+                    if (c < upto)
+                        st_remote_f64(r_halo + (uint32_t)((blk % HR) * 32 + G::tcol(c & 31)) * 8u, row[G::tcol(c & 31)]);
+                    __syncwarp();
+                    if (lane == 0) st_remote_u32_release(r_halo_cols, (unsigned)upto);
+                } else {
+                    if (c < upto) ll_store(out + c, row[G::tcol(c & 31)], P.epoch);
+                }
                 sent = upto;
                 if (sent == blk_end) { // all 32 columns of this block are out: the stage may drain
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[st]);
-                    blk_end += 32;
+                    blk++;
                     if (++st == nst) st = 0;
                     row = last_row + st * stage_doubles;
                 }
@@ -697,26 +801,40 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, uint64_t *don
 }
 
 // ---------------------------------------------------------------------- kernel ----
-template <int KIND, bool DOT>
+template <int KIND, bool DOT, bool MASKED>
 __global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
-    __shared__ int s_strip;
+    __shared__ int s_ticket;
     __shared__ int s_dead;
     __shared__ unsigned s_counters[2]; // [0] columns finished by the last row, [1] hand-off columns received
     double *smem = reinterpret_cast<double *>(smem_raw);
-    double *halo_s = smem + P.nst * P.nt * TILE_DOUBLES; // [nst][32] hand-off rows
+    double *halo_s = smem + P.nst * P.nt * TILE_DOUBLES; // [HR][32] hand-off ring
     uint64_t *full = bars, *done = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = P.cs > 1 ? cluster_ctarank() : 0;
 
+    // Strips are handed out in ticket order, one ticket per cluster (taken first, so the
+    // global count stays consistent even for gated launches): a running CTA only ever
+    // waits on strips that are already running or finished.
     if (threadIdx.x == 0) {
-        // ticket first (keeps the global count consistent even for gated launches)
-        const unsigned long long tk = atomicAdd(P.ticket, 1ULL);
-        const int sj = (int)(tk - P.ticket_base);
-        s_strip = sj;
+        if (rank == 0) s_ticket = (int)(atomicAdd(P.ticket, 1ULL) - P.ticket_base);
         s_dead = 0;
         s_counters[0] = 0;
         s_counters[1] = 0;
+    }
+    __syncthreads();
+    int ticket;
+    if (P.cs > 1) {
+        cluster_sync_all(); // every CTA of the cluster is resident, its counters are zero, rank 0's ticket is set
+        ticket = (int)ld_remote_u32(mapa(smem_u32(&s_ticket), 0));
+    } else {
+        ticket = s_ticket;
+    }
+    const int sj = ticket * P.cs + (int)rank;
+    if (sj >= P.nby) return;                 // padding CTA of the last cluster
+    if (P.gated && P.scal->done) return;     // the solve has converged: nothing to do
+    if (threadIdx.x == 0) {
         const bool publish = sj + 1 < P.nby;
         for (int i = 0; i < P.nst; i++) {
             mbar_init(&full[i], 1);                // loader's expect_tx arrival (+ TMA bytes)
@@ -725,14 +843,14 @@ __global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepP
         }
         fence_mbar_init();
     }
-    // the first strip has no upstream row: its hand-off rows read +0.0
-    for (int i = threadIdx.x; i < P.nst * 32; i += blockDim.x) halo_s[i] = 0.0;
+    // the very first strip has no upstream row: its hand-off rows read +0.0
+    if (sj == 0)
+        for (int i = threadIdx.x; i < HR * 32; i += blockDim.x) halo_s[i] = 0.0;
     __syncthreads();
-    if (P.gated && P.scal->done) return;
-    const int sj = s_strip;
 
     if (warp == 0) {
         unsigned long long t0 = 0;
+        const long long c0 = clock64();
         if (P.times && lane == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
         compute_warp<KIND, DOT>(P, smem, halo_s, full, done, sj, lane, &s_dead, s_counters);
         if (P.times && lane == 0) {
@@ -740,14 +858,16 @@ __global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepP
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
             P.times[16 * sj] = t0;
             P.times[16 * sj + 1] = t1;
+            P.times[16 * sj + 15] = (unsigned long long)(clock64() - c0); // SM cycles spent by the compute warp
         }
     } else if (warp == 1) {
         loader_warp<KIND>(P, smem, full, empty, sj, lane, &s_dead);
     } else if (warp == 2) {
-        storer_warp<KIND, DOT>(P, smem, done, empty, sj, lane, &s_dead);
+        storer_warp<KIND, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
     } else if (warp == 3) {
-        if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, done, sj, lane, &s_dead, s_counters);
-    } else if (sj > 0) {
+        if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank);
+    } else if (sj > 0 && rank == 0) {
+        // first strip of a cluster: its upstream strip lives in another cluster and talks through L2
         poller_warp<KIND>(P, halo_s, sj, lane, &s_dead, s_counters);
     }
 }
@@ -820,6 +940,15 @@ int sweep_init(ifl_ctx *c) {
     IFL_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned long long)));
     IFL_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned long long)));
     IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 16 * sizeof(unsigned long long)));
+    // Hand-off through cluster DSMEM is implemented and bit-exact, but measured SLOWER than the
+    // L2 message path on B200 (4096^2 backward sweep: 825 us with clusters of 8 vs 672 us
+    // without; the cluster-scope release store costs the publisher ~1.4 us per group, see
+    // profiles/r01_c_dsmem_experiment.txt).  Default: no clusters; IFL_SWEEP_CLUSTER=2|4|8 enables.
+    c->sweep_cluster = 1;
+    if (const char *e = getenv("IFL_SWEEP_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
+    }
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -869,19 +998,44 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         c->epoch++;
         P.epoch = 1;
     }
+    P.cs = c->sweep_cluster;
+    const int n_clusters = (P.nby + P.cs - 1) / P.cs;
     P.ticket = c->ticket;
-    P.ticket_base = c->sweep_launches * (unsigned long long)P.nby;
+    P.ticket_base = c->sweep_tickets;
+    c->sweep_tickets += (unsigned long long)n_clusters;
     c->sweep_launches++;
     P.scal = c->scal;
     P.times = c->sweep_times;
-    const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)nst * 32 * sizeof(double);
-    static bool attr_set[5][2] = {{false, false}, {false, false}, {false, false}, {false, false}, {false, false}};
-    if (!attr_set[KIND][DOT]) {
-        IFL_CUDA(cudaFuncSetAttribute(k_sweep<KIND, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        attr_set[KIND][DOT] = true;
+    const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double);
+    const bool masked = P.mask_tile >= 0;
+    static bool attr_set[5][2][2];
+    if (!attr_set[KIND][DOT][masked]) {
+        IFL_CUDA(masked ? cudaFuncSetAttribute(k_sweep<KIND, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               227 * 1024 - 1024)
+                        : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               227 * 1024 - 1024));
+        attr_set[KIND][DOT][masked] = true;
     }
     ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
-    k_sweep<KIND, DOT><<<P.nby, 160, smem, c->stream>>>(P);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
+    cfg.blockDim = dim3(160);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = P.cs > 1 ? 1 : 0;
+    const cudaError_t le = masked ? cudaLaunchKernelEx(&cfg, k_sweep<KIND, DOT, true>, P)
+                                  : cudaLaunchKernelEx(&cfg, k_sweep<KIND, DOT, false>, P);
+    if (le != cudaSuccess) {
+        set_error("sweep launch (cluster %d) -> %s", P.cs, cudaGetErrorString(le));
+        return IFL_E_CUDA;
+    }
     IFL_LAUNCHED(c);
     return IFL_OK;
 }

@@ -27,6 +27,7 @@ if len(t) > 1:
     print("first lags (us):", [round(float(x) / 1e3, 2) for x in np.diff(end)[:6]])
 print("strip 0 duration %.1f us -> %.1f ns/step" % (dur[0] / 1e3, dur[0] / steps))
 print("total %.1f us" % (end.max() / 1e3))
+print("strip 0: %.1f SM cycles/step, SM clock during the sweep %.0f MHz" % (t[0, 15] / steps, t[0, 15] / dur[0] * 1e3))
 print("end-to-end lag between consecutive strips (us): mean %.2f  min %.2f  max %.2f" %
       (np.diff(end).mean() / 1e3, np.diff(end).min() / 1e3, np.diff(end).max() / 1e3))
 print("start lag (us): mean %.2f" % (np.diff(start).mean() / 1e3))
@@ -40,4 +41,4 @@ print("hand-off of the group ending at column %d (us): producer done -> publishe
 for i in range(1, min(6, len(t))):
     a, b, c, d = t[i - 1, 11], t[i - 1, 12], t[i, 13], t[i, 14]
     print("  strip %d->%d: publish +%.2f  receive +%.2f  consume +%.2f   (total %.2f)" %
-          (i - 1, i, (b - a) / 1e3, (c - b) / 1e3, (d - c) / 1e3, (d - a) / 1e3))
+          (i - 1, i, (b - a) / 1e3, (c - b) / 1e3 if c else float("nan"), (d - c) / 1e3 if c else float("nan"), (d - a) / 1e3))
