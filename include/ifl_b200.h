@@ -69,6 +69,8 @@ typedef enum {
     IFL_BUF_ADIAG,  /* FluidSolver::_aDiag  v3:204 */
     IFL_BUF_APLUSX, /* FluidSolver::_aPlusX v3:205 */
     IFL_BUF_APLUSY, /* FluidSolver::_aPlusY v3:206 */
+    IFL_BUF_UDENSITY, /* FluidSolver::_uDensity v7:598, (w+1)*h */
+    IFL_BUF_VDENSITY, /* FluidSolver::_vDensity v7:599, w*(h+1) */
     IFL_BUF_COUNT_
 } ifl_buf;
 
@@ -163,6 +165,19 @@ typedef enum { IFL_AUX_VOLUME = 0, IFL_AUX_NORMAL_X, IFL_AUX_NORMAL_Y, IFL_AUX_P
 size_t ifl_aux_elems(const ifl_ctx *ctx, int field, int which);
 int ifl_aux_download(ifl_ctx *ctx, int field, int which, void *host);
 int ifl_aux_upload(ifl_ctx *ctx, int field, int which, const void *host);
+
+/* ---- chapters 6+: heat diffusion, buoyancy, variable density ------------------- */
+/* FluidSolver(w,h,rhoAir,rhoSoot,diffusion,bodies) ctor arguments (v6:921); ambient
+ * temperature 294 K and g = 9.81 are the reference's constants (v6:932-933). */
+int ifl_set_fluid_params(ifl_ctx *ctx, double rho_air, double rho_soot, double diffusion);
+double ifl_ambient_t(const ifl_ctx *ctx);                 /* FluidSolver::ambientT v6:1017 */
+int ifl_build_heat_matrix(ifl_ctx *ctx, double timestep); /* buildHeatDiffusionMatrix v6:683-712 */
+int ifl_add_buoyancy(ifl_ctx *ctx, double timestep);      /* addBuoyancy v6:881-895 */
+int ifl_compute_densities(ifl_ctx *ctx);                  /* computeDensities v7:658-675 */
+/* FluidSolver::addInflow(x,y,w,h,d,t,u,v) v6:1010-1015 */
+int ifl_add_inflow_t(ifl_ctx *ctx, double x, double y, double w, double h, double d, double t, double u, double v);
+/* For chapters 6+ ifl_update ignores `density` (uses ifl_set_fluid_params) and fills
+ * infos[0] (heat solve) and infos[1] (pressure solve). */
 
 /* ---- FluidSolver private hot-path methods ----------------------------------- */
 int ifl_build_rhs(ifl_ctx *ctx);                                         /* v3:208-217 */

@@ -44,6 +44,8 @@ EXPORTS = [
     "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
     "ifl_set_bodies", "ifl_fill_solid_fields", "ifl_set_boundary_condition", "ifl_extrapolate",
     "ifl_aux_elems", "ifl_aux_download", "ifl_aux_upload",
+    "ifl_set_fluid_params", "ifl_ambient_t", "ifl_build_heat_matrix", "ifl_add_buoyancy", "ifl_compute_densities",
+    "ifl_add_inflow_t",
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
     "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
     "ifl_project", "ifl_project_gs", "ifl_apply_pressure",
@@ -101,6 +103,13 @@ def load_library():
     L.ifl_aux_elems.argtypes = [vp, ci, ci]
     L.ifl_aux_download.argtypes = [vp, ci, ci, vp]
     L.ifl_aux_upload.argtypes = [vp, ci, ci, vp]
+    L.ifl_set_fluid_params.argtypes = [vp, cd, cd, cd]
+    L.ifl_ambient_t.restype = cd
+    L.ifl_ambient_t.argtypes = [vp]
+    L.ifl_build_heat_matrix.argtypes = [vp, cd]
+    L.ifl_add_buoyancy.argtypes = [vp, cd]
+    L.ifl_compute_densities.argtypes = [vp]
+    L.ifl_add_inflow_t.argtypes = [vp, cd, cd, cd, cd, cd, cd, cd, cd]
     L.ifl_build_rhs.argtypes = [vp]
     L.ifl_build_pressure_matrix.argtypes = [vp, cd, cd]
     L.ifl_build_preconditioner.argtypes = [vp]
@@ -159,6 +168,7 @@ class SolidSphere(SolidBody):  # v4:204-209: SolidSphere(x, y, s, t, vx, vy, vt)
 
 
 AUX = {"volume": 0, "normalX": 1, "normalY": 2, "phi": 3, "cell": 4, "body": 5}
+BUF.update({"uDensity": 16, "vDensity": 17})
 
 
 class FluidSolver:
@@ -173,7 +183,10 @@ class FluidSolver:
     bodies between updates and update() re-reads them.
     """
 
-    def __init__(self, w, h, density, version=3, device=0, bodies=None):
+    def __init__(self, w, h, density, version=3, device=0, bodies=None, rho_soot=None, diffusion=None):
+        """Chapters 1-5: FluidSolver(w, h, density[, bodies]).  Chapters 6-7:
+        FluidSolver(w, h, rhoAir, rhoSoot, diffusion, bodies) (v6:921) -- pass rhoAir as
+        `density` plus rho_soot= and diffusion=."""
         self.L = load_library()
         self.w, self.h, self.density, self.version = w, h, density, version
         self.hx = 1.0 / min(w, h)
@@ -186,6 +199,22 @@ class FluidSolver:
         self.bodies = bodies if bodies is not None else []
         if version >= 4:
             self.syncBodies()
+        if version >= 6:
+            self._chk(self.L.ifl_set_fluid_params(self.ctx, density, rho_soot, diffusion))
+        self.last_heat = None
+
+    # ---- chapters 6+
+    def ambientT(self):
+        return self.L.ifl_ambient_t(self.ctx)
+
+    def buildHeatDiffusionMatrix(self, timestep):
+        self._chk(self.L.ifl_build_heat_matrix(self.ctx, timestep))
+
+    def addBuoyancy(self, timestep):
+        self._chk(self.L.ifl_add_buoyancy(self.ctx, timestep))
+
+    def computeDensities(self):
+        self._chk(self.L.ifl_compute_densities(self.ctx))
 
     # ---- chapters 4+
     def syncBodies(self):
@@ -309,6 +338,8 @@ class FluidSolver:
             return "Exiting solver after %d iterations, maximum %s is %f" % (info.iterations, what, info.max_error)
         if info.status == 1:
             return "Exceeded budget of %d iterations, maximum %s was %f" % (info.iterations, what, info.max_error)
+        if self.version >= 6:
+            return "Initial guess sufficiently small"  # v6:835
         return None  # v3:355-356 returns silently
 
     def project(self, limit, timestep=None):
@@ -339,13 +370,25 @@ class FluidSolver:
         self._chk(self.L.ifl_quantity_add_inflow(self.ctx, FIELD[field], x0, y0, x1, y1, v))
 
     # ---- public surface
-    def addInflow(self, x, y, w, h, d, u, v):
-        self._chk(self.L.ifl_add_inflow(self.ctx, x, y, w, h, d, u, v))
+    def addInflow(self, x, y, w, h, d, *rest):
+        if self.version >= 6:  # addInflow(x, y, w, h, d, t, u, v)  v6:1010
+            t, u, v = rest
+            self._chk(self.L.ifl_add_inflow_t(self.ctx, x, y, w, h, d, t, u, v))
+        else:
+            u, v = rest
+            self._chk(self.L.ifl_add_inflow(self.ctx, x, y, w, h, d, u, v))
 
     def update(self, timestep):
-        info = SolveInfo()
         if self.version >= 4:
             self.syncBodies()
+        if self.version >= 6:
+            infos = (SolveInfo * 2)()
+            self._chk(self.L.ifl_update(self.ctx, timestep, self.density, infos))
+            self._record(infos[0])
+            self.last_heat = self.last
+            self._record(infos[1])
+            return self.last
+        info = SolveInfo()
         self._chk(self.L.ifl_update(self.ctx, timestep, self.density, ctypes.byref(info)))
         self._record(info)
         return self.last

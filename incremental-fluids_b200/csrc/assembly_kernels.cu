@@ -199,6 +199,149 @@ __global__ void __launch_bounds__(256) k_apply_pressure_v_solid(Arr v, Arr p, Fi
     v.p[iv] = val;
 }
 
+// ---------------------------------------------------------- chapters 6+ (heat, density) ----
+// buildHeatDiffusionMatrix, gather form of v6:683-712: aDiag starts at 1.0 everywhere and
+// collects +scale per fluid-fluid face in raster order of the scattering cell.
+__global__ void __launch_bounds__(256) k_heat_matrix(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int w = aDiag.w, h = aDiag.h;
+    if (x >= w || y >= h) return;
+    const int cp = d.src.pitch;
+    const size_t ic = x + (size_t)y * cp;
+    double diag = 1.0, ax = 0.0, ay = 0.0;
+    if (d.cell[ic] == CELL_FLUID) {
+        if (y > 0 && d.cell[ic - cp] == CELL_FLUID) diag += scale;
+        if (x > 0 && d.cell[ic - 1] == CELL_FLUID) diag += scale;
+        if (x < w - 1 && d.cell[ic + 1] == CELL_FLUID) {
+            diag += scale;
+            ax = -scale;
+        }
+        if (y < h - 1 && d.cell[ic + cp] == CELL_FLUID) {
+            diag += scale;
+            ay = -scale;
+        }
+    }
+    const size_t i = x + (size_t)y * aDiag.pitch;
+    aDiag.p[i] = diag;
+    aPlusX.p[i] = ax;
+    aPlusY.p[i] = ay;
+}
+
+// addBuoyancy (v6:881-895), gather form: v face (x,y) receives the upper cell's half first
+// (that cell is earlier in raster order), then the lower cell's half.  Not masked.
+__global__ void __launch_bounds__(256) k_add_buoyancy(Arr v, Arr dsrc, Arr tsrc, double tg, double alpha, double tAmb) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int H = dsrc.h;
+    if (x >= v.w || y > H) return;
+    const size_t iv = x + (size_t)y * v.pitch;
+    double val = v.p[iv];
+    if (y > 0) {
+        const size_t i = x + (size_t)(y - 1) * dsrc.pitch;
+        const double b = tg * (alpha * dsrc.p[i] - (tsrc.p[i] - tAmb) / tAmb);
+        val += b * 0.5;
+    }
+    if (y < H) {
+        const size_t i = x + (size_t)y * dsrc.pitch;
+        const double b = tg * (alpha * dsrc.p[i] - (tsrc.p[i] - tAmb) / tAmb);
+        val += b * 0.5;
+    }
+    v.p[iv] = val;
+}
+
+// computeDensities (v7:658-675): face density = sum of the halves of the adjacent cells
+__device__ __forceinline__ double cell_density(const Arr &dsrc, const Arr &tsrc, int x, int y, double rhoAir, double tAmb,
+                                               double alpha) {
+    const size_t i = x + (size_t)y * dsrc.pitch;
+    const double density = rhoAir * tAmb / tsrc.p[i] * (1.0 + alpha * dsrc.p[i]);
+    return std_max(density, 0.05 * rhoAir);
+}
+__global__ void __launch_bounds__(256) k_density_u(Arr ud, Arr dsrc, Arr tsrc, double rhoAir, double tAmb, double alpha) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int W = dsrc.w;
+    if (x > W || y >= ud.h) return;
+    double val = 0.0;
+    if (x > 0) val += 0.5 * cell_density(dsrc, tsrc, x - 1, y, rhoAir, tAmb, alpha);
+    if (x < W) val += 0.5 * cell_density(dsrc, tsrc, x, y, rhoAir, tAmb, alpha);
+    ud.p[x + (size_t)y * ud.pitch] = val;
+}
+__global__ void __launch_bounds__(256) k_density_v(Arr vd, Arr dsrc, Arr tsrc, double rhoAir, double tAmb, double alpha) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int H = dsrc.h;
+    if (x >= vd.w || y > H) return;
+    double val = 0.0;
+    if (y > 0) val += 0.5 * cell_density(dsrc, tsrc, x, y - 1, rhoAir, tAmb, alpha);
+    if (y < H) val += 0.5 * cell_density(dsrc, tsrc, x, y, rhoAir, tAmb, alpha);
+    vd.p[x + (size_t)y * vd.pitch] = val;
+}
+
+// element `flat` of the reference's DENSE vDensity array (w columns per row)
+__device__ __forceinline__ double vdens_flat(const Arr &vd, int flat) { return vd.p[(flat % vd.w) + (size_t)(flat / vd.w) * vd.pitch]; }
+
+// buildPressureMatrix with variable density (v7:680-707), gather form.  The reference indexes
+// _vDensity with _u->idx (row stride w+1 instead of w); kept.
+__global__ void __launch_bounds__(256) k_build_matrix_density(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, Field u,
+                                                              Field v, Arr ud, Arr vd, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int w = aDiag.w, h = aDiag.h;
+    if (x >= w || y >= h) return;
+    const int cp = d.src.pitch;
+    const size_t ic = x + (size_t)y * cp;
+    double diag = 0.0, ax = 0.0, ay = 0.0;
+    if (d.cell[ic] == CELL_FLUID) {
+        const size_t iu = x + (size_t)y * u.src.pitch;
+        const size_t iv = x + (size_t)y * v.src.pitch;
+        if (y > 0 && d.cell[ic - cp] == CELL_FLUID) diag += scale * v.volume.p[iv] / vdens_flat(vd, x + y * (w + 1));
+        if (x > 0 && d.cell[ic - 1] == CELL_FLUID) diag += scale * u.volume.p[iu] / ud.p[x + (size_t)y * ud.pitch];
+        if (x < w - 1 && d.cell[ic + 1] == CELL_FLUID) {
+            const double factor = scale * u.volume.p[iu + 1] / ud.p[x + 1 + (size_t)y * ud.pitch];
+            diag += factor;
+            ax = -factor;
+        }
+        if (y < h - 1 && d.cell[ic + cp] == CELL_FLUID) {
+            const double factor = scale * v.volume.p[iv + v.src.pitch] / vdens_flat(vd, x + (y + 1) * (w + 1));
+            diag += factor;
+            ay = -factor;
+        }
+    }
+    const size_t i = x + (size_t)y * aDiag.pitch;
+    aDiag.p[i] = diag;
+    aPlusX.p[i] = ax;
+    aPlusY.p[i] = ay;
+}
+
+// applyPressure with face densities (v7:891-906)
+__global__ void __launch_bounds__(256) k_apply_pressure_u_density(Arr u, Arr p, Field d, Arr ud, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int W = p.w;
+    if (x > W || y >= u.h) return;
+    const size_t iu = x + (size_t)y * u.pitch;
+    const size_t ic = x + (size_t)y * d.src.pitch;
+    const double dens = ud.p[x + (size_t)y * ud.pitch];
+    double val = u.p[iu];
+    if (x > 0 && d.cell[ic - 1] == CELL_FLUID) val += scale * p.p[x - 1 + (size_t)y * p.pitch] / dens;
+    if (x < W && d.cell[ic] == CELL_FLUID) val -= scale * p.p[x + (size_t)y * p.pitch] / dens;
+    u.p[iu] = val;
+}
+__global__ void __launch_bounds__(256) k_apply_pressure_v_density(Arr v, Arr p, Field d, Arr vd, double scale) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int H = p.h;
+    if (x >= v.w || y > H) return;
+    const size_t iv = x + (size_t)y * v.pitch;
+    const size_t ic = x + (size_t)y * d.src.pitch;
+    const double dens = vd.p[x + (size_t)y * vd.pitch];
+    double val = v.p[iv];
+    if (y > 0 && d.cell[ic - d.src.pitch] == CELL_FLUID) val += scale * p.p[x + (size_t)(y - 1) * p.pitch] / dens;
+    if (y < H && d.cell[ic] == CELL_FLUID) val -= scale * p.p[x + (size_t)y * p.pitch] / dens;
+    v.p[iv] = val;
+}
+
 static dim3 grid2d(int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); }
 
 int launch_build_rhs(ifl_ctx *c) {
@@ -218,7 +361,13 @@ int launch_build_rhs(ifl_ctx *c) {
 int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = timestep / (density * c->hx * c->hx);
-    if (c->version >= 4)
+    if (c->version >= 7) {
+        const double scale7 = timestep / (c->hx * c->hx); // v7:681
+        k_build_matrix_density<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
+                                                                           c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
+                                                                           c->fd[IFL_FIELD_V], c->uDensity, c->vDensity,
+                                                                           scale7);
+    } else if (c->version >= 4)
         k_build_matrix_solid<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
                                                                          c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
                                                                          c->fd[IFL_FIELD_V], scale, c->version >= 5);
@@ -232,6 +381,16 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = timestep / (density * c->hx);
     Field &u = c->fd[IFL_FIELD_U], &v = c->fd[IFL_FIELD_V];
+    if (c->version >= 7) {
+        const double scale7 = timestep / c->hx; // v7:892
+        k_apply_pressure_u_density<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], c->uDensity,
+                                                                             scale7);
+        IFL_LAUNCHED(c);
+        k_apply_pressure_v_density<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], c->vDensity,
+                                                                             scale7);
+        IFL_LAUNCHED(c);
+        return IFL_OK;
+    }
     if (c->version >= 4) {
         k_apply_pressure_u_solid<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], scale);
         IFL_LAUNCHED(c);
@@ -242,6 +401,35 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
     k_apply_pressure_u<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, scale, 1);
     IFL_LAUNCHED(c);
     k_apply_pressure_v<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, scale, 1);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_build_heat_matrix(ifl_ctx *c, double timestep) { // v6:683-712
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double scale = c->diffusion * timestep * 1.0 / (c->hx * c->hx);
+    k_heat_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, c->fd[IFL_FIELD_D], scale);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_add_buoyancy(ifl_ctx *c, double timestep) { // v6:881-895
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double alpha = (c->rho_soot - c->rho_air) / c->rho_air;
+    Field &v = c->fd[IFL_FIELD_V];
+    k_add_buoyancy<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->fd[IFL_FIELD_D].src, c->fd[IFL_FIELD_T].src,
+                                                            timestep * c->g, alpha, c->t_amb);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_compute_densities(ifl_ctx *c) { // v7:658-675
+    ProfScope ps_(c, IFL_K_ASSEMBLY);
+    const double alpha = (c->rho_soot - c->rho_air) / c->rho_air;
+    Arr &ds = c->fd[IFL_FIELD_D].src, &ts = c->fd[IFL_FIELD_T].src;
+    k_density_u<<<grid2d(c->uDensity.w, c->uDensity.h), 256, 0, c->stream>>>(c->uDensity, ds, ts, c->rho_air, c->t_amb, alpha);
+    IFL_LAUNCHED(c);
+    k_density_v<<<grid2d(c->vDensity.w, c->vDensity.h), 256, 0, c->stream>>>(c->vDensity, ds, ts, c->rho_air, c->t_amb, alpha);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }

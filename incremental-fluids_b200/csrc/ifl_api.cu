@@ -131,6 +131,8 @@ static Arr *buf_arr(ifl_ctx *c, int buf) {
     case IFL_BUF_ADIAG: return &c->aDiag;
     case IFL_BUF_APLUSX: return &c->aPlusX;
     case IFL_BUF_APLUSY: return &c->aPlusY;
+    case IFL_BUF_UDENSITY: return c->version >= 7 ? &c->uDensity : nullptr;
+    case IFL_BUF_VDENSITY: return c->version >= 7 ? &c->vDensity : nullptr;
     }
     return nullptr;
 }
@@ -163,8 +165,8 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
         return IFL_E_ARG;
     }
-    if (version > 5) {
-        set_error("ifl_create: chapter %d (heat, variable density, FLIP) is not available in this build", version);
+    if (version > 7) {
+        set_error("ifl_create: chapter %d (FLIP) is not available in this build", version);
         return IFL_E_ARG;
     }
     int ndev = 0;
@@ -192,6 +194,16 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
         if ((rc = alloc_field(c->fd[IFL_FIELD_D], w, h, 0.5, 0.5, solids)) != IFL_OK) break;
         if ((rc = alloc_field(c->fd[IFL_FIELD_U], w + 1, h, 0.0, 0.5, solids)) != IFL_OK) break;
         if ((rc = alloc_field(c->fd[IFL_FIELD_V], w, h + 1, 0.5, 0.0, solids)) != IFL_OK) break;
+        if (version >= 6) { // temperature field at ambient temperature, v6:921-941
+            c->t_amb = 294.0;
+            c->g = 9.81;
+            if ((rc = alloc_field(c->fd[IFL_FIELD_T], w, h, 0.5, 0.5, true)) != IFL_OK) break;
+            if ((rc = fill_arr(c->fd[IFL_FIELD_T].src, c->t_amb)) != IFL_OK) break;
+        }
+        if (version >= 7) {
+            if ((rc = alloc_arr(c->uDensity, w + 1, h)) != IFL_OK) break;
+            if ((rc = alloc_arr(c->vDensity, w, h + 1)) != IFL_OK) break;
+        }
         if (solids) {
             if ((rc = alloc_arr(c->pe, w, h)) != IFL_OK) break;
             if ((rc = alloc_arr(c->fmask, w, h)) != IFL_OK) break;
@@ -238,6 +250,8 @@ int ifl_destroy(ifl_ctx *c) {
     for (int i = 0; i < 4; i++) free_field(c->fd[i]);
     free_arr(c->pe);
     free_arr(c->fmask);
+    free_arr(c->uDensity);
+    free_arr(c->vDensity);
     if (c->bodies_d) cudaFree(c->bodies_d);
     if (c->ext_ready) cudaFree(c->ext_ready);
     Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
@@ -451,6 +465,57 @@ int ifl_extrapolate(ifl_ctx *c, int field) {
     TRY(need_solids(c, "ifl_extrapolate"));
     TRY(check_field(c, field));
     return launch_extrapolate(c, field);
+}
+
+// ---- chapters 6+: heat and variable density ----------------------------------------------
+static int need_heat(ifl_ctx *c, const char *what) {
+    if (c->version < 6) {
+        set_error("%s: heat / buoyancy belong to chapters 6+", what);
+        return IFL_E_ARG;
+    }
+    return IFL_OK;
+}
+
+int ifl_set_fluid_params(ifl_ctx *c, double rho_air, double rho_soot, double diffusion) {
+    CHECK_CTX(c);
+    TRY(need_heat(c, "ifl_set_fluid_params"));
+    c->rho_air = rho_air;
+    c->rho_soot = rho_soot;
+    c->diffusion = diffusion;
+    return IFL_OK;
+}
+
+double ifl_ambient_t(const ifl_ctx *c) { return c ? c->t_amb : 0.0; }
+
+int ifl_build_heat_matrix(ifl_ctx *c, double timestep) {
+    CHECK_CTX(c);
+    TRY(need_heat(c, "ifl_build_heat_matrix"));
+    return launch_build_heat_matrix(c, timestep);
+}
+
+int ifl_add_buoyancy(ifl_ctx *c, double timestep) {
+    CHECK_CTX(c);
+    TRY(need_heat(c, "ifl_add_buoyancy"));
+    return launch_add_buoyancy(c, timestep);
+}
+
+int ifl_compute_densities(ifl_ctx *c) {
+    CHECK_CTX(c);
+    if (c->version < 7) {
+        set_error("ifl_compute_densities: variable density belongs to chapters 7+");
+        return IFL_E_ARG;
+    }
+    return launch_compute_densities(c);
+}
+
+int ifl_add_inflow_t(ifl_ctx *c, double x, double y, double w, double h, double d, double t, double u, double v) {
+    CHECK_CTX(c);
+    TRY(need_heat(c, "ifl_add_inflow_t"));
+    TRY(launch_add_inflow(c, IFL_FIELD_D, x, y, x + w, y + h, d)); // v6:1010-1015
+    TRY(launch_add_inflow(c, IFL_FIELD_T, x, y, x + w, y + h, t));
+    TRY(launch_add_inflow(c, IFL_FIELD_U, x, y, x + w, y + h, u));
+    TRY(launch_add_inflow(c, IFL_FIELD_V, x, y, x + w, y + h, v));
+    return IFL_OK;
 }
 
 // aux arrays of a FluidQuantity: doubles (volume, normals, phi) or bytes (cell, body)
@@ -671,10 +736,43 @@ static int update_solids(ifl_ctx *c, double timestep, double density, ifl_solve_
     return IFL_OK;
 }
 
+// FluidSolver::update of chapters 6-7 (v7:995-1034, v6:966-1008): heat solve, buoyancy,
+// (face densities,) pressure solve, advection of d, t, u, v.  infos[0] = heat solve,
+// infos[1] = pressure solve.
+static int update_heat(ifl_ctx *c, double timestep, ifl_solve_info *infos) {
+    const int fields[4] = {IFL_FIELD_D, IFL_FIELD_T, IFL_FIELD_U, IFL_FIELD_V};
+    ifl_solve_info local[2];
+    if (!infos) infos = local;
+    for (int i = 0; i < 4; i++) TRY(launch_fill_solid_fields(c, fields[i]));
+    Arr &tsrc = c->fd[IFL_FIELD_T].src;
+    IFL_CUDA(cudaMemcpyAsync(c->r.p, tsrc.p, c->r.bytes(), cudaMemcpyDeviceToDevice, c->stream)); // v7:1001
+    TRY(launch_build_heat_matrix(c, timestep));
+    TRY(launch_mic0_factor(c));
+    TRY(pcg_project(c, 2000, &infos[0]));
+    IFL_CUDA(cudaMemcpyAsync(tsrc.p, c->p.p, c->p.bytes(), cudaMemcpyDeviceToDevice, c->stream)); // v7:1005
+    TRY(launch_extrapolate(c, IFL_FIELD_T));
+    TRY(launch_add_buoyancy(c, timestep));
+    TRY(launch_set_boundary_condition(c));
+    TRY(launch_build_rhs(c));
+    if (c->version >= 7) TRY(launch_compute_densities(c));
+    TRY(launch_build_matrix(c, timestep, c->rho_air));
+    TRY(launch_mic0_factor(c));
+    TRY(pcg_project(c, 2000, &infos[1]));
+    TRY(launch_apply_pressure(c, timestep, c->rho_air));
+    TRY(launch_extrapolate(c, IFL_FIELD_D));
+    TRY(launch_extrapolate(c, IFL_FIELD_U));
+    TRY(launch_extrapolate(c, IFL_FIELD_V));
+    TRY(launch_set_boundary_condition(c));
+    for (int i = 0; i < 4; i++) TRY(launch_advect(c, fields[i], timestep));
+    for (int i = 0; i < 4; i++) TRY(ifl_flip(c, fields[i]));
+    return IFL_OK;
+}
+
 int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
     CHECK_CTX(c);
     ifl_solve_info local;
     ifl_solve_info *info = infos ? infos : &local;
+    if (c->version >= 6) return update_heat(c, timestep, infos);
     if (c->version >= 4) return update_solids(c, timestep, density, info);
     TRY(launch_build_rhs(c));
     if (pcg_chapter(c)) { // v3:433-447

@@ -76,6 +76,9 @@ struct ifl_ctx {
     ifl::Arr r, p, z, s, q, precon, aDiag, aPlusX, aPlusY, cx, cy;
     ifl::Arr pe;    // chapters 4+: precon with +0.0 at non-fluid cells (what the masked sweeps multiply by)
     ifl::Arr fmask; // chapters 4+: 1.0 at fluid cells of _d, 0.0 elsewhere (operand of the masked factorisation)
+    ifl::Arr uDensity, vDensity; // chapter 7+: densities on the staggered faces (v7:598-599)
+    double rho_air, rho_soot, diffusion; // chapters 6+ ctor arguments (v6:921)
+    double t_amb, g;                      // 294.0, 9.81 (v6:932-933)
     ifl::BodyDev *bodies_d; // [MAX_BODIES]
     int n_bodies;
     int *ext_ready;         // extrapolate(): device counter of cells resolved in the last batch of rounds
@@ -205,6 +208,9 @@ int launch_build_rhs(ifl_ctx *c);
 int launch_build_matrix(ifl_ctx *c, double timestep, double density);
 int launch_apply_pressure(ifl_ctx *c, double timestep, double density);
 int launch_add_inflow(ifl_ctx *c, int field, double x0, double y0, double x1, double y1, double v);
+int launch_build_heat_matrix(ifl_ctx *c, double timestep);
+int launch_add_buoyancy(ifl_ctx *c, double timestep);
+int launch_compute_densities(ifl_ctx *c);
 // advect_kernels.cu
 int launch_advect(ifl_ctx *c, int field, double timestep);
 

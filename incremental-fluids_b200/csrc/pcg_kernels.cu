@@ -33,6 +33,14 @@ static int vec_blocks(const Arr &a) {
     return (int)(g.x * g.y);
 }
 
+// Chapters 6+ mask dotProduct / scaledAdd / infinityNorm with `cell == CELL_FLUID`
+// (v6:781-826); matrixVectorProduct stays unmasked (v6:791).  `cell` is _d's byte array
+// (row pitch == the vectors' pitch) or null for the unmasked chapters.
+struct CellMask {
+    const uint8_t *cell;
+    __device__ __forceinline__ bool fluid(size_t i) const { return !cell || cell[i] == CELL_FLUID; }
+};
+
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
@@ -41,7 +49,7 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 template <bool WITH_DOT>
 __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDiag, Arr aPlusX, Arr aPlusY,
                                                          double *__restrict__ partials,
-                                                         const SolveScalars *__restrict__ gate) {
+                                                         const SolveScalars *__restrict__ gate, CellMask mk) {
     if (gate && gate->done) return;
     __shared__ double red[32];
     const int W = dst.w, H = dst.h, pitch = dst.pitch;
@@ -98,12 +106,12 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
         if (x + 1 < W) {
             st2(dst.p + x + row, make_double2(t0, t1));
             if (WITH_DOT) {
-                acc += t0 * b_c.x;
-                acc += t1 * b_c.y;
+                if (mk.fluid(x + row)) acc += t0 * b_c.x;
+                if (mk.fluid(x + 1 + row)) acc += t1 * b_c.y;
             }
         } else if (x < W) {
             dst.p[x + row] = t0;
-            if (WITH_DOT) acc += t0 * b_c.x;
+            if (WITH_DOT && mk.fluid(x + row)) acc += t0 * b_c.x;
         }
         b_up = b_c;
         b_c = b_dn;
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
 
 // p += alpha*s ; r += q*(-alpha) ; partial[block] = max|r|     v3:363-366
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r, Arr q, const SolveScalars *sc,
-                                                             double *__restrict__ partials) {
+                                                             double *__restrict__ partials, CellMask mk) {
     if (sc->done) return;
     __shared__ double red[32];
     const double alpha = sc->alpha;
@@ -132,14 +140,19 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
         for (int y = y0; y < y1; y++) {
             const size_t i = x + (size_t)y * pitch;
             double2 pv = ld2(p.p + i), sv = ld2(s.p + i), rv = ld2(r.p + i), qv = ld2(q.p + i);
-            pv.x = pv.x + sv.x * alpha;
-            pv.y = pv.y + sv.y * alpha;
-            rv.x = rv.x + qv.x * nalpha;
-            rv.y = rv.y + qv.y * nalpha;
+            const bool f0 = mk.fluid(i), f1 = mk.fluid(i + 1);
+            if (f0) {
+                pv.x = pv.x + sv.x * alpha;
+                rv.x = rv.x + qv.x * nalpha;
+                m = std_max(m, fabs(rv.x));
+            }
+            if (f1) {
+                pv.y = pv.y + sv.y * alpha;
+                rv.y = rv.y + qv.y * nalpha;
+                m = std_max(m, fabs(rv.y)); // pad column (x+1 == W) holds 0 -> no effect
+            }
             st2(p.p + i, pv);
             st2(r.p + i, rv);
-            m = std_max(m, fabs(rv.x));
-            m = std_max(m, fabs(rv.y)); // pad column (x+1 == W) holds 0 -> no effect
         }
     }
     m = block_reduce<true>(m, red);
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
 // dst = a + b*scale, scale either immediate or read from the device scalars (beta)
 template <bool BETA_FROM_SCALARS>
 __global__ void __launch_bounds__(VEC_THREADS) k_scaled_add(Arr dst, Arr a, Arr b, double scale,
-                                                             const SolveScalars *sc) {
+                                                             const SolveScalars *sc, CellMask mk) {
     if (BETA_FROM_SCALARS) {
         if (sc->done) return;
         scale = sc->beta;
@@ -163,12 +176,17 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scaled_add(Arr dst, Arr a, Arr 
     for (int y = y0; y < y1; y++) {
         const size_t i = x + (size_t)y * pitch;
         const double2 av = ld2(a.p + i), bv = ld2(b.p + i);
-        st2(dst.p + i, make_double2(av.x + bv.x * scale, av.y + bv.y * scale));
+        if (!mk.cell) {
+            st2(dst.p + i, make_double2(av.x + bv.x * scale, av.y + bv.y * scale));
+        } else { // masked cells keep dst (which may alias a or b)
+            if (mk.fluid(i)) dst.p[i] = av.x + bv.x * scale;
+            if (mk.fluid(i + 1)) dst.p[i + 1] = av.y + bv.y * scale;
+        }
     }
 }
 
 template <bool IS_MAX>
-__global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *__restrict__ partials) {
+__global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *__restrict__ partials, CellMask mk) {
     __shared__ double red[32];
     const int W = a.w, H = a.h, pitch = a.pitch;
     const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
@@ -179,13 +197,14 @@ __global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *_
         for (int y = y0; y < y1; y++) {
             const size_t i = x + (size_t)y * pitch;
             const double2 av = ld2(a.p + i);
+            const bool f0 = mk.fluid(i), f1 = mk.fluid(i + 1);
             if (IS_MAX) {
-                acc = std_max(acc, fabs(av.x));
-                acc = std_max(acc, fabs(av.y));
+                if (f0) acc = std_max(acc, fabs(av.x));
+                if (f1) acc = std_max(acc, fabs(av.y));
             } else {
                 const double2 bv = ld2(b.p + i);
-                acc += av.x * bv.x;
-                acc += av.y * bv.y;
+                if (f0) acc += av.x * bv.x;
+                if (f1) acc += av.y * bv.y;
             }
         }
     }
@@ -229,16 +248,24 @@ __global__ void __launch_bounds__(1024) k_scalar(const double *__restrict__ part
 }
 
 // ------------------------------------------------------------------ launchers ----
+static CellMask mask_of(ifl_ctx *c) {
+    CellMask m;
+    m.cell = c->version >= 6 ? c->fd[IFL_FIELD_D].cell : nullptr;
+    return m;
+}
+
 
 
 int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
     ProfScope ps_(c, IFL_K_MATVEC);
     dim3 g = vec_grid(dst);
     if (with_dot) {
-        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, c->partials, c->scal);
+        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, c->partials, c->scal,
+                                                         mask_of(c));
         c->n_partials = vec_blocks(dst);
     } else {
-        k_matvec<false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, nullptr, nullptr);
+        k_matvec<false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, nullptr, nullptr,
+                                                          mask_of(c));
     }
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -246,7 +273,7 @@ int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
 
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, c->partials);
+    k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, c->partials, mask_of(c));
     c->n_partials = vec_blocks(a);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -254,7 +281,7 @@ int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
 
 int launch_inf_norm(ifl_ctx *c, const Arr &a) {
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_reduce2<true><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, a, c->partials);
+    k_reduce2<true><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, a, c->partials, mask_of(c));
     c->n_partials = vec_blocks(a);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -262,7 +289,7 @@ int launch_inf_norm(ifl_ctx *c, const Arr &a) {
 
 int launch_scaled_add(ifl_ctx *c, const Arr &dst, const Arr &a, const Arr &b, double s) {
     ProfScope ps_(c, IFL_K_XPAY);
-    k_scaled_add<false><<<vec_grid(dst), VEC_THREADS, 0, c->stream>>>(dst, a, b, s, nullptr);
+    k_scaled_add<false><<<vec_grid(dst), VEC_THREADS, 0, c->stream>>>(dst, a, b, s, nullptr, mask_of(c));
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -306,7 +333,8 @@ static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
     {
         ProfScope ps_(c, IFL_K_AXPY2_NORM);
-        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, c->partials);
+        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, c->partials,
+                                                                    mask_of(c));
         c->n_partials = vec_blocks(c->p);
         IFL_LAUNCHED(c);
     }
@@ -316,7 +344,7 @@ static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(scalar_stage<SC_BETA>(c));
     {
         ProfScope ps_(c, IFL_K_XPAY);
-        k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal);
+        k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
         IFL_LAUNCHED(c);
     }
     return IFL_OK;
