@@ -117,6 +117,8 @@ typedef enum {
     IFL_K_ASSEMBLY,     /* buildRhs, buildPressureMatrix, applyPressure, addInflow */
     IFL_K_ADVECT,       /* FluidQuantity::advect              v2:170-183 */
     IFL_K_GS_SWEEP,     /* one Gauss-Seidel sweep             v2:239-268 */
+    IFL_K_P2G,          /* FluidQuantity::fromParticles       v8:663-688 */
+    IFL_K_G2P,          /* gridToParticles, diff, undiff      v8:904-911, 379-388 */
     IFL_K_COUNT_
 } ifl_kernel_class;
 /* Start (on != 0) / stop per-class event timing; starting resets the accumulators. */
@@ -178,6 +180,27 @@ int ifl_compute_densities(ifl_ctx *ctx);                  /* computeDensities v7
 int ifl_add_inflow_t(ifl_ctx *ctx, double x, double y, double w, double h, double d, double t, double u, double v);
 /* For chapters 6+ ifl_update ignores `density` (uses ifl_set_fluid_params) and fills
  * infos[0] (heat solve) and infos[1] (pressure solve). */
+
+/* ---- chapter 8: FLIP particle <-> grid transfers -------------------------------- */
+/* The particle set is ParticleQuantities' SoA (v8:717-723): posX, posY and one property
+ * array per registered quantity in the order d, t, u, v (v8:1309-1312); capacity w*h*12.
+ * Particle bookkeeping (init/count/prune/seed, v8:735-813) stays on the host side of this
+ * boundary for now: upload the set, run the transfers on the device, download it. */
+int ifl_particles_capacity(const ifl_ctx *ctx);
+int ifl_particles_upload(ifl_ctx *ctx, int count, const double *pos_x, const double *pos_y, const double *prop_d,
+                         const double *prop_t, const double *prop_u, const double *prop_v);
+int ifl_particles_download(ifl_ctx *ctx, int *count, double *pos_x, double *pos_y, double *prop_d, double *prop_t,
+                           double *prop_u, double *prop_v);
+/* FluidQuantity::fromParticles (v8:663-688): P2G of one quantity, contributions summed in
+ * ascending particle index like the reference; marks particle-free fluid cells CELL_EMPTY (2). */
+int ifl_from_particles(ifl_ctx *ctx, int field);
+/* ParticleQuantities::gridToParticles(alpha) v8:904-911 */
+int ifl_grid_to_particles(ifl_ctx *ctx, double alpha);
+int ifl_quantity_copy(ifl_ctx *ctx, int field);                   /* FluidQuantity::copy   v8:374 (_old == the *_DST buffer) */
+int ifl_quantity_diff(ifl_ctx *ctx, int field, double alpha);     /* FluidQuantity::diff   v8:379 */
+int ifl_quantity_undiff(ifl_ctx *ctx, int field, double alpha);   /* FluidQuantity::undiff v8:385 */
+/* ParticleQuantities::advect(timestep, u, v) v8:931-939 */
+int ifl_particles_advect(ifl_ctx *ctx, double timestep);
 
 /* ---- FluidSolver private hot-path methods ----------------------------------- */
 int ifl_build_rhs(ifl_ctx *ctx);                                         /* v3:208-217 */

@@ -35,7 +35,7 @@ BUF = {name: i for i, name in enumerate(
 FIELD = {"d": 0, "u": 1, "v": 2, "t": 3}
 # mirrors enum ifl_kernel_class
 KERNEL_CLASSES = ["matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "scalar", "factor", "assembly",
-                  "advect", "gs_sweep"]
+                  "advect", "gs_sweep", "p2g", "g2p"]
 
 EXPORTS = [
     "ifl_create", "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
@@ -46,6 +46,8 @@ EXPORTS = [
     "ifl_aux_elems", "ifl_aux_download", "ifl_aux_upload",
     "ifl_set_fluid_params", "ifl_ambient_t", "ifl_build_heat_matrix", "ifl_add_buoyancy", "ifl_compute_densities",
     "ifl_add_inflow_t",
+    "ifl_particles_capacity", "ifl_particles_upload", "ifl_particles_download", "ifl_from_particles",
+    "ifl_grid_to_particles", "ifl_quantity_copy", "ifl_quantity_diff", "ifl_quantity_undiff", "ifl_particles_advect",
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
     "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
     "ifl_project", "ifl_project_gs", "ifl_apply_pressure",
@@ -110,6 +112,15 @@ def load_library():
     L.ifl_add_buoyancy.argtypes = [vp, cd]
     L.ifl_compute_densities.argtypes = [vp]
     L.ifl_add_inflow_t.argtypes = [vp, cd, cd, cd, cd, cd, cd, cd, cd]
+    L.ifl_particles_capacity.argtypes = [vp]
+    L.ifl_particles_upload.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
+    L.ifl_particles_download.argtypes = [vp, ctypes.POINTER(ci), vp, vp, vp, vp, vp, vp]
+    L.ifl_from_particles.argtypes = [vp, ci]
+    L.ifl_grid_to_particles.argtypes = [vp, cd]
+    L.ifl_quantity_copy.argtypes = [vp, ci]
+    L.ifl_quantity_diff.argtypes = [vp, ci, cd]
+    L.ifl_quantity_undiff.argtypes = [vp, ci, cd]
+    L.ifl_particles_advect.argtypes = [vp, cd]
     L.ifl_build_rhs.argtypes = [vp]
     L.ifl_build_pressure_matrix.argtypes = [vp, cd, cd]
     L.ifl_build_preconditioner.argtypes = [vp]
@@ -202,6 +213,37 @@ class FluidSolver:
         if version >= 6:
             self._chk(self.L.ifl_set_fluid_params(self.ctx, density, rho_soot, diffusion))
         self.last_heat = None
+
+    # ---- chapter 8 (FLIP): ParticleQuantities' transfers
+    def setParticles(self, posX, posY, props):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in [posX, posY] + list(props)]
+        self._particles_keepalive = arrs
+        self._chk(self.L.ifl_particles_upload(self.ctx, arrs[0].size, *[a.ctypes.data for a in arrs]))
+
+    def getParticles(self):
+        n = ctypes.c_int()
+        self._chk(self.L.ifl_particles_download(self.ctx, ctypes.byref(n), None, None, None, None, None, None))
+        out = [np.empty(n.value) for _ in range(6)]
+        self._chk(self.L.ifl_particles_download(self.ctx, ctypes.byref(n), *[a.ctypes.data for a in out]))
+        return out[0], out[1], out[2:]
+
+    def fromParticles(self, field):
+        self._chk(self.L.ifl_from_particles(self.ctx, FIELD[field]))
+
+    def gridToParticles(self, alpha):
+        self._chk(self.L.ifl_grid_to_particles(self.ctx, alpha))
+
+    def copy(self, field):
+        self._chk(self.L.ifl_quantity_copy(self.ctx, FIELD[field]))
+
+    def diff(self, field, alpha):
+        self._chk(self.L.ifl_quantity_diff(self.ctx, FIELD[field], alpha))
+
+    def undiff(self, field, alpha):
+        self._chk(self.L.ifl_quantity_undiff(self.ctx, FIELD[field], alpha))
+
+    def particlesAdvect(self, timestep):
+        self._chk(self.L.ifl_particles_advect(self.ctx, timestep))
 
     # ---- chapters 6+
     def ambientT(self):

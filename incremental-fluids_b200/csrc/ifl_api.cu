@@ -165,10 +165,7 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
         return IFL_E_ARG;
     }
-    if (version > 7) {
-        set_error("ifl_create: chapter %d (FLIP) is not available in this build", version);
-        return IFL_E_ARG;
-    }
+
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("ifl_create: no CUDA device (%s); libifl_b200 has no CPU path", cudaGetErrorString(cudaGetLastError()));
@@ -230,6 +227,7 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
             break;
         }
         if ((rc = sweep_init(c)) != IFL_OK) break;
+        if (version >= 8 && (rc = flip_init(c)) != IFL_OK) break;
         if (cudaDeviceSynchronize() != cudaSuccess) {
             set_error("ifl_create: %s", cudaGetErrorString(cudaGetLastError()));
             rc = IFL_E_CUDA;
@@ -267,6 +265,7 @@ int ifl_destroy(ifl_ctx *c) {
         free(c->prof_cls);
     }
     sweep_free(c);
+    flip_free(c);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c);
     return IFL_OK;
@@ -516,6 +515,77 @@ int ifl_add_inflow_t(ifl_ctx *c, double x, double y, double w, double h, double 
     TRY(launch_add_inflow(c, IFL_FIELD_U, x, y, x + w, y + h, u));
     TRY(launch_add_inflow(c, IFL_FIELD_V, x, y, x + w, y + h, v));
     return IFL_OK;
+}
+
+// ---- chapter 8: FLIP -----------------------------------------------------------------------
+static int need_flip(ifl_ctx *c, const char *what) {
+    if (c->version < 8) {
+        set_error("%s: particles belong to chapter 8", what);
+        return IFL_E_ARG;
+    }
+    return IFL_OK;
+}
+
+int ifl_particles_capacity(const ifl_ctx *c) { return (c && c->version >= 8) ? c->W * c->H * 12 : 0; }
+
+int ifl_particles_upload(ifl_ctx *c, int count, const double *px, const double *py, const double *pd, const double *pt,
+                         const double *pu, const double *pv) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_upload"));
+    if (count > 0 && (!px || !py)) {
+        set_error("ifl_particles_upload: null position array");
+        return IFL_E_ARG;
+    }
+    const double *props[4] = {pd, pt, pu, pv};
+    return flip_set_particles(c, count, px, py, props);
+}
+
+int ifl_particles_download(ifl_ctx *c, int *count, double *px, double *py, double *pd, double *pt, double *pu,
+                           double *pv) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_download"));
+    double *props[4] = {pd, pt, pu, pv};
+    return flip_get_particles(c, count, px, py, props);
+}
+
+int ifl_from_particles(ifl_ctx *c, int field) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_from_particles"));
+    TRY(check_field(c, field));
+    return launch_from_particles(c, field);
+}
+
+int ifl_grid_to_particles(ifl_ctx *c, double alpha) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_grid_to_particles"));
+    return launch_grid_to_particles(c, alpha);
+}
+
+int ifl_quantity_copy(ifl_ctx *c, int field) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_quantity_copy"));
+    TRY(check_field(c, field));
+    return launch_copy(c, field);
+}
+
+int ifl_quantity_diff(ifl_ctx *c, int field, double alpha) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_quantity_diff"));
+    TRY(check_field(c, field));
+    return launch_diff(c, field, alpha, 0);
+}
+
+int ifl_quantity_undiff(ifl_ctx *c, int field, double alpha) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_quantity_undiff"));
+    TRY(check_field(c, field));
+    return launch_diff(c, field, alpha, 1);
+}
+
+int ifl_particles_advect(ifl_ctx *c, double timestep) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_advect"));
+    return launch_particles_advect(c, timestep);
 }
 
 // aux arrays of a FluidQuantity: doubles (volume, normals, phi) or bytes (cell, body)
@@ -772,6 +842,12 @@ int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *info
     CHECK_CTX(c);
     ifl_solve_info local;
     ifl_solve_info *info = infos ? infos : &local;
+    if (c->version >= 8) {
+        set_error("ifl_update: the chapter-8 step needs particle bookkeeping (seed/prune, v8:754-813) and the "
+                  "order-dependent empty-cell extrapolation (v8:611-651), which are not on the device yet; "
+                  "drive the stages individually");
+        return IFL_E_ARG;
+    }
     if (c->version >= 6) return update_heat(c, timestep, infos);
     if (c->version >= 4) return update_solids(c, timestep, density, info);
     TRY(launch_build_rhs(c));

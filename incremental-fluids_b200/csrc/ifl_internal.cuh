@@ -82,6 +82,7 @@ struct ifl_ctx {
     ifl::BodyDev *bodies_d; // [MAX_BODIES]
     int n_bodies;
     int *ext_ready;         // extrapolate(): device counter of cells resolved in the last batch of rounds
+    void *particles;        // chapter 8: ifl::ParticleSet (flip_kernels.cu)
     double *partials;          // [MAX_PARTIALS] block partials (sum or max)
     int n_partials;            // valid entries written by the last reducing kernel
     ifl::SolveScalars *scal;   // device
@@ -203,6 +204,16 @@ int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve
 int launch_fill_solid_fields(ifl_ctx *c, int field);
 int launch_set_boundary_condition(ifl_ctx *c);
 int launch_extrapolate(ifl_ctx *c, int field);
+// flip_kernels.cu (chapter 8)
+int flip_init(ifl_ctx *c);
+void flip_free(ifl_ctx *c);
+int flip_set_particles(ifl_ctx *c, int count, const double *posX, const double *posY, const double *const *props);
+int flip_get_particles(ifl_ctx *c, int *count, double *posX, double *posY, double *const *props);
+int launch_from_particles(ifl_ctx *c, int field);
+int launch_grid_to_particles(ifl_ctx *c, double alpha);
+int launch_copy(ifl_ctx *c, int field);
+int launch_diff(ifl_ctx *c, int field, double alpha, int undo);
+int launch_particles_advect(ifl_ctx *c, double timestep);
 // assembly_kernels.cu
 int launch_build_rhs(ifl_ctx *c);
 int launch_build_matrix(ifl_ctx *c, double timestep, double density);

@@ -124,7 +124,13 @@ API void *ref_create(int w, int h, const double *params, int nparams, const doub
 
 API void ref_destroy(void *p) {
     Handle *hd = (Handle *)p;
+#if REF_VER < 8
     delete hd->s;
+#else
+    /* ~ParticleQuantities (v8:887-888) delete[]s its FluidQuantity pointers instead of its
+     * property arrays -- undefined behaviour that aborts under glibc.  The reference's main()
+     * never destroys its solver either; leak it. */
+#endif
     /* SolidBody has a protected virtual destructor in the reference; leak the few bytes. */
     delete hd;
 }
