@@ -96,6 +96,7 @@ struct ifl_ctx {
     unsigned long long sweep_launches; // sweeps launched so far
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
+    int sweep_v2;                      // triangular solves use sweep2_kernels.cu
     void *map_cache;                   // TMA tensor maps keyed by array base pointer
     unsigned long long *sweep_times_buf; // [strips][2] diagnostics buffer
     unsigned long long *sweep_times;     // == sweep_times_buf while ifl_debug_sweep_times is armed, else null
@@ -200,6 +201,9 @@ int launch_mic0_factor(ifl_ctx *c);
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
+// sweep2_kernels.cu
+int launch_precon_forward2(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
+int launch_precon_backward2(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 // solid_kernels.cu (chapters 4+)
 int launch_fill_solid_fields(ifl_ctx *c, int field);
 int launch_set_boundary_condition(ifl_ctx *c);

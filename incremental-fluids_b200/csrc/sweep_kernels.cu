@@ -43,6 +43,7 @@
 //     (the reference skips those terms, v3:280-283), so the inner loop has no
 //     boundary predicates at all.  Pad results are never stored.
 #include "ifl_internal.cuh"
+#include "sweep_common.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -65,8 +66,6 @@ constexpr int MAX_TILES = 7;
 constexpr int MAX_STAGES = 8;
 constexpr int HG = 8; // hand-off granularity in columns (publisher and consumer side)
 constexpr int HR = 16; // hand-off ring depth in blocks (512 columns): deep enough that back-pressure never binds
-constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
-constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
 
 struct TileDesc {
     double *p;     // array base (pitched) -- used by the storer
@@ -94,172 +93,6 @@ struct SweepParams {
     int cs;           // thread-block cluster size (1 = no cluster): strips of one cluster hand off through DSMEM
     unsigned long long *times; // diagnostics: [nby][2] globaltimer ns at strip start / end (or null)
 };
-
-// ------------------------------------------------------------------ PTX helpers ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: every dependency wait in this file gives up after a (very long) poll
-// budget, raises the watchdog flags and lets the kernel run to completion with garbage,
-// so that a protocol bug can never hang the device.  `dead` is a CTA-wide shared flag.
-__device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity, volatile int *dead, SolveScalars *scal) {
-    if (mbar_try(bar, parity)) return;
-    if (*dead) return;
-    unsigned n = 0;
-    while (!mbar_try(bar, parity)) {
-        if (++n > WATCHDOG_TRIES || *dead) {
-            *dead = 1;
-            scal->watchdog = 1;
-            return;
-        }
-    }
-}
-// TMA: one 2-D box global -> shared, completion counted in bytes on an mbarrier.
-// Out-of-range rows (y = -1 for the first strip) are filled with zeros by the hardware.
-__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// ---- thread-block cluster / distributed shared memory
-__device__ __forceinline__ unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local_addr` (a shared::cta address of THIS CTA's layout) in CTA `rank`
-__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, unsigned rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_remote_f64(uint32_t raddr, double v) {
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
-}
-__device__ __forceinline__ void st_remote_u32_release(uint32_t raddr, unsigned v) {
-    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_remote_u32(uint32_t raddr) {
-    unsigned v;
-    asm volatile("ld.relaxed.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(raddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u32_acquire(uint32_t a) { // pairs with st_remote_u32_release
-    unsigned v;
-    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-
-// NCCL-LL style message: {lo, epoch, hi, epoch} in one 16-byte store / load.
-__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch) {
-    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
-                 : "memory");
-}
-__device__ __forceinline__ bool ll_load(const uint4 *src, unsigned epoch, double &v) {
-    unsigned a, b, c, d;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
-    v = __hiloint2double((int)c, (int)a);
-    return b == epoch && d == epoch;
-}
-
-// Shared-memory accessors on 32-bit shared-space byte addresses: the per-step address is
-// `selected base + compile-time offset`, which ptxas folds into the instruction's
-// immediate field, so a step spends one ISETP + one SEL on addressing.
-__device__ __forceinline__ double lds_f64(uint32_t a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void lds_f64_if(double &v, uint32_t a, bool pred) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.u32 p, %2, 0;\n\t"
-        "@p ld.shared.f64 %0, [%1];\n\t"
-        "}"
-        : "+d"(v)
-        : "r"(a), "r"((unsigned)pred)
-        : "memory");
-}
-__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
-// store only if `pred` (EDGE macro-steps: lanes outside the strip run the same code, unbranched)
-template <bool ALWAYS>
-__device__ __forceinline__ void sts_f64_p(uint32_t a, double v, bool pred) {
-    if (ALWAYS) {
-        sts_f64(a, v);
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.u32 p, %2, 0;\n\t"
-            "@p st.shared.f64 [%0], %1;\n\t"
-            "}" ::"r"(a),
-            "d"(v), "r"((unsigned)pred)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void sts_u32_volatile(uint32_t a, unsigned v) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_u32_volatile(uint32_t a) {
-    unsigned v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-// Bounded spin until the shared counter at `a` reaches `need`.
-__device__ __forceinline__ void wait_counter(uint32_t a, unsigned need, volatile int *dead, SolveScalars *scal) {
-    if (lds_u32_acquire(a) >= need) return;
-    unsigned n = 0;
-    while (lds_u32_acquire(a) < need) {
-        if (++n > WATCHDOG_POLLS || *dead) {
-            *dead = 1;
-            scal->watchdog = 1;
-            return;
-        }
-    }
-}
-__device__ __forceinline__ double sel_f64(bool pred, double a, double b) { // pred ? a : b, one select deep
-    double r;
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.u32 p, %3, 0;\n\t"
-        "selp.f64 %0, %1, %2, p;\n\t"
-        "}"
-        : "=d"(r)
-        : "d"(a), "d"(b), "r"((unsigned)pred));
-    return r;
-}
 
 // ---------------------------------------------------------------- compute warp ----
 template <int KIND>
@@ -325,6 +158,7 @@ struct GsConst {
     int yvalid;            // y < H
     int W;
     int ncols;             // padded sweep width (32 * nbx)
+    int cluster;           // hand-off counter is bumped remotely (DSMEM): needs acquire loads
 };
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
@@ -434,7 +268,10 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next, dead, scal); // lane 0 is about to touch block m+1
         // lane 0 is about to fetch the first hand-off value of the next group of HG columns
         if (((kk + 1) % HG) == 0 && has_up && EDGE != 2) {
-            wait_counter(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
+            if (gs.cluster)
+                wait_counter<true>(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
+            else
+                wait_counter<false>(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
             if (times && lane == 0 && 32 * m + kk + 1 + HG == probe) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(times[14]));
         }
         // ---- critical path first: the upper neighbour's value of the previous step
@@ -493,12 +330,18 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.yvalid = y < P.H ? 1 : 0;
         gs.W = P.W;
         gs.ncols = P.nbx * 32;
+        gs.cluster = P.cs > 1 ? 1 : 0;
     }
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
     mbar_wait(&full[0], 0, dead, P.scal);
-    if (has_up) wait_counter(halo_cols_addr, HG, dead, P.scal);
+    if (has_up) {
+        if (P.cs > 1)
+            wait_counter<true>(halo_cols_addr, HG, dead, P.scal);
+        else
+            wait_counter<false>(halo_cols_addr, HG, dead, P.scal);
+    }
     fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
     if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
@@ -889,20 +732,21 @@ static PFN_encodeTiled encode_fn() {
     return fn;
 }
 
-// Tensor map of one pitched cell array: 2-D, double, box = 32 columns x 33 rows, no
+// Tensor map of one pitched cell array: 2-D, double, box = box_w columns x 33 rows, no
 // swizzle (the skewed access pattern is conflict-free on dense rows), zero OOB fill.
 // Maps are cached per base pointer (flip() only swaps pointers).
 struct MapCache {
-    enum { N = 32 };
+    enum { N = 64 };
     void *key[N];
+    int box_w[N];
     CUtensorMap map[N];
     int n;
 };
 
-static int get_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
+int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
     MapCache *mc = (MapCache *)c->map_cache;
     for (int i = 0; i < mc->n; i++)
-        if (mc->key[i] == a.p) {
+        if (mc->key[i] == a.p && mc->box_w[i] == box_w) {
             *out = mc->map[i];
             return IFL_OK;
         }
@@ -913,7 +757,7 @@ static int get_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)a.pitch, (cuuint64_t)a.rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)a.pitch * sizeof(double)};
-    const cuuint32_t box[2] = {32, (cuuint32_t)TROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, 33u};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.p, gdim, gstride, box, estr,
@@ -925,6 +769,7 @@ static int get_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
     }
     if (mc->n < MapCache::N) {
         mc->key[mc->n] = a.p;
+        mc->box_w[mc->n] = box_w;
         mc->map[mc->n] = m;
         mc->n++;
     }
@@ -949,6 +794,11 @@ int sweep_init(ifl_ctx *c) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
     }
+    // the two-columns-per-step kernels (sweep2_kernels.cu) serve the triangular solves unless
+    // IFL_SWEEP_V1=1 asks for the one-column engine of this file (kept for A/B measurements)
+    c->sweep_v2 = 1;
+    if (const char *e = getenv("IFL_SWEEP_V1"))
+        if (atoi(e) == 1) c->sweep_v2 = 0;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -982,7 +832,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         P.t[k].store = spec[k].store;
         P.t[k].p2 = spec[k].a2 ? spec[k].a2->p : nullptr;
         if (spec[k].load) {
-            int rc = get_map(c, *spec[k].a, &P.map[k]);
+            int rc = sweep_get_map(c, *spec[k].a, 32, &P.map[k]);
             if (rc != IFL_OK) return rc;
         }
     }
@@ -1060,6 +910,7 @@ int launch_mic0_factor(ifl_ctx *c) {
 static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
+    if (c->sweep_v2) return launch_precon_forward2(c, dst, a, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
@@ -1073,6 +924,7 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
+    if (c->sweep_v2) return launch_precon_backward2(c, dst, r_for_dot, with_dot, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
