@@ -97,6 +97,26 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device);
 /* FluidSolver dtor (v3:418-431). */
 int ifl_destroy(ifl_ctx *ctx);
 const char *ifl_last_error(void);
+
+/* ---- row-slab multi-GPU (one process per GPU) --------------------------
+ * Rank `rank` of `world` (<= 8) owns a slab of whole 32-row strips of every array and
+ * runs on `device`.  All ranks map the slabs of all ranks into one address range (CUDA
+ * virtual memory management, handles passed over the UNIX socket `rendezvous`, which
+ * rank 0 binds), so kernels address neighbours' rows over NVLink; MIC(0) stays exact: the
+ * wavefront crosses slab boundaries through the same hand-off messages it uses between
+ * strips.  Results are bit-identical to the one-GPU context on every rank.
+ * Collective calls (every rank, same order): create/destroy, upload/download/fill, every
+ * compute entry point.  ifl_download returns the WHOLE array on every rank; ifl_upload and
+ * ifl_update_host move only the caller's slab rows of the (whole-array) host buffers.
+ * Chapters 1-3 so far. */
+int ifl_create_dist(ifl_ctx **out, int w, int h, int version, int device, int rank, int world, const char *rendezvous);
+/* Slab of `rank`: cell rows [row0, row1) (pure host arithmetic). */
+int ifl_dist_plan(int h, int world, int rank, int *row0, int *row1);
+int ifl_dist_info(const ifl_ctx *ctx, int *rank, int *world, int *row0, int *row1);
+/* Device barrier across the ranks on the context's stream, then host synchronisation. */
+int ifl_dist_barrier(ifl_ctx *ctx);
+/* Host-only self-test of the rendezvous / descriptor passing (no CUDA involved). */
+int ifl_dist_selftest(int rank, int world, const char *rendezvous);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long ifl_launch_count(const ifl_ctx *ctx);
 /* The CUDA stream (cudaStream_t as void*) every kernel of this context is launched on. */

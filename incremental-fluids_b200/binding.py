@@ -38,7 +38,8 @@ KERNEL_CLASSES = ["matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "s
                   "advect", "gs_sweep", "p2g", "g2p"]
 
 EXPORTS = [
-    "ifl_create", "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
+    "ifl_create", "ifl_create_dist", "ifl_dist_plan", "ifl_dist_info", "ifl_dist_barrier", "ifl_dist_selftest",
+    "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
     "ifl_profile", "ifl_profile_read", "ifl_debug_sweep_times",
     "ifl_buf_elems", "ifl_upload", "ifl_download", "ifl_fill",
     "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
@@ -80,6 +81,11 @@ def load_library():
     vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
     L.ifl_last_error.restype = ctypes.c_char_p
     L.ifl_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci]
+    L.ifl_create_dist.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci, ctypes.c_char_p]
+    L.ifl_dist_plan.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.ifl_dist_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.ifl_dist_barrier.argtypes = [vp]
+    L.ifl_dist_selftest.argtypes = [ci, ci, ctypes.c_char_p]
     L.ifl_destroy.argtypes = [vp]
     L.ifl_launch_count.restype = ctypes.c_longlong
     L.ifl_launch_count.argtypes = [vp]
@@ -194,16 +200,25 @@ class FluidSolver:
     bodies between updates and update() re-reads them.
     """
 
-    def __init__(self, w, h, density, version=3, device=0, bodies=None, rho_soot=None, diffusion=None):
+    def __init__(self, w, h, density, version=3, device=0, bodies=None, rho_soot=None, diffusion=None,
+                 rank=0, world=1, rendezvous=None):
         """Chapters 1-5: FluidSolver(w, h, density[, bodies]).  Chapters 6-7:
         FluidSolver(w, h, rhoAir, rhoSoot, diffusion, bodies) (v6:921) -- pass rhoAir as
-        `density` plus rho_soot= and diffusion=."""
+        `density` plus rho_soot= and diffusion=.
+
+        world > 1: row-slab multi-GPU, one process per GPU (ifl_create_dist); `rendezvous` is
+        a UNIX socket path shared by the ranks.  Every method is then a collective call."""
         self.L = load_library()
         self.w, self.h, self.density, self.version = w, h, density, version
         self.hx = 1.0 / min(w, h)
+        self.rank, self.world = rank, world
         ctx = ctypes.c_void_p()
         self.ctx = None
-        self._chk(self.L.ifl_create(ctypes.byref(ctx), w, h, version, device))
+        if world > 1:
+            self._chk(self.L.ifl_create_dist(ctypes.byref(ctx), w, h, version, device, rank, world,
+                                             rendezvous.encode()))
+        else:
+            self._chk(self.L.ifl_create(ctypes.byref(ctx), w, h, version, device))
         self.ctx = ctx
         self.last = None
         self.messages = []  # the stdout lines the reference would have printed
@@ -285,6 +300,15 @@ class FluidSolver:
         if a.size != self.L.ifl_aux_elems(self.ctx, FIELD[field], AUX[which]):
             raise ValueError("size mismatch for %s.%s" % (field, which))
         self._chk(self.L.ifl_aux_upload(self.ctx, FIELD[field], AUX[which], a.ctypes.data))
+
+    def rows(self):
+        """Cell rows [row0, row1) of this rank's slab (the whole grid on one GPU)."""
+        r0, r1 = ctypes.c_int(), ctypes.c_int()
+        self._chk(self.L.ifl_dist_info(self.ctx, None, None, ctypes.byref(r0), ctypes.byref(r1)))
+        return r0.value, r1.value
+
+    def barrier(self):
+        self._chk(self.L.ifl_dist_barrier(self.ctx))
 
     def _chk(self, rc):
         if rc != 0:

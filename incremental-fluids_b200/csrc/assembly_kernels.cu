@@ -18,8 +18,8 @@ namespace ifl {
 // r = -(1/hx) * (u[x+1,y] - u[x,y] + v[x,y+1] - v[x,y])            v3:213-214
 __global__ void __launch_bounds__(256) k_build_rhs(Arr r, Arr u, Arr v, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= r.w || y >= r.h) return;
+    const int y = r.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= r.w || y >= r.ry1) return;
     const double ul = u.p[x + (size_t)y * u.pitch];
     const double ur = u.p[x + 1 + (size_t)y * u.pitch];
     const double vt = v.p[x + (size_t)y * v.pitch];
@@ -32,9 +32,9 @@ __global__ void __launch_bounds__(256) k_build_rhs(Arr r, Arr u, Arr v, double s
 // (its x-branch), then the cell's own x-branch and y-branch.
 __global__ void __launch_bounds__(256) k_build_matrix(Arr aDiag, Arr aPlusX, Arr aPlusY, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = aDiag.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int w = aDiag.w, h = aDiag.h;
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= aDiag.ry1) return;
     double diag = 0.0;
     if (y > 0) diag += scale;
     if (x > 0) diag += scale;
@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(256) k_build_matrix(Arr aDiag, Arr aPlusX, Arr
 // and then "-= scale*p[x,y]" (cell x).  v3:387-388; wall faces zeroed v3:394-395.
 __global__ void __launch_bounds__(256) k_apply_pressure_u(Arr u, Arr p, double scale, int zero_walls) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = u.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int W = p.w;
-    if (x > W || y >= u.h) return;
+    if (x > W || y >= u.ry1) return;
     const size_t iu = x + (size_t)y * u.pitch;
     double val = u.p[iu];
     if (x > 0) val += scale * p.p[x - 1 + (size_t)y * p.pitch];
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(256) k_apply_pressure_u(Arr u, Arr p, double s
 // v face (x,y), y in [0,H]: "+= scale*p[x,y-1]" then "-= scale*p[x,y]".  v3:389-390, 396-397.
 __global__ void __launch_bounds__(256) k_apply_pressure_v(Arr v, Arr p, double scale, int zero_walls) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = v.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = p.h;
-    if (x >= v.w || y > H) return;
+    if (x >= v.w || y >= v.ry1) return; // v has H+1 rows; the last slab owns row H
     const size_t iv = x + (size_t)y * v.pitch;
     double val = v.p[iv];
     if (y > 0) val += scale * p.p[x + (size_t)(y - 1) * p.pitch];
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(256) k_build_matrix_solid(Arr aDiag, Arr aPlus
 // applyPressure with solid cells (v4:796-810): only fluid cells push on their faces.
 __global__ void __launch_bounds__(256) k_apply_pressure_u_solid(Arr u, Arr p, Field d, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = u.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int W = p.w;
-    if (x > W || y >= u.h) return;
+    if (x > W || y >= u.ry1) return;
     const size_t iu = x + (size_t)y * u.pitch;
     const size_t ic = x + (size_t)y * d.src.pitch;
     double val = u.p[iu];
@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(256) k_apply_pressure_u_solid(Arr u, Arr p, Fi
 
 __global__ void __launch_bounds__(256) k_apply_pressure_v_solid(Arr v, Arr p, Field d, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = v.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = p.h;
-    if (x >= v.w || y > H) return;
+    if (x >= v.w || y >= v.ry1) return; // v has H+1 rows; the last slab owns row H
     const size_t iv = x + (size_t)y * v.pitch;
     const size_t ic = x + (size_t)y * d.src.pitch;
     double val = v.p[iv];
@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(256) k_build_matrix_density(Arr aDiag, Arr aPl
 // applyPressure with face densities (v7:891-906)
 __global__ void __launch_bounds__(256) k_apply_pressure_u_density(Arr u, Arr p, Field d, Arr ud, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = u.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int W = p.w;
-    if (x > W || y >= u.h) return;
+    if (x > W || y >= u.ry1) return;
     const size_t iu = x + (size_t)y * u.pitch;
     const size_t ic = x + (size_t)y * d.src.pitch;
     const double dens = ud.p[x + (size_t)y * ud.pitch];
@@ -330,9 +330,9 @@ __global__ void __launch_bounds__(256) k_apply_pressure_u_density(Arr u, Arr p, 
 }
 __global__ void __launch_bounds__(256) k_apply_pressure_v_density(Arr v, Arr p, Field d, Arr vd, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = v.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = p.h;
-    if (x >= v.w || y > H) return;
+    if (x >= v.w || y >= v.ry1) return; // v has H+1 rows; the last slab owns row H
     const size_t iv = x + (size_t)y * v.pitch;
     const size_t ic = x + (size_t)y * d.src.pitch;
     const double dens = vd.p[x + (size_t)y * vd.pitch];
@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(256) k_apply_pressure_v_density(Arr v, Arr p, 
 }
 
 static dim3 grid2d(int w, int h) { return dim3((w + 63) / 64, (h + 3) / 4); }
+// grid over the rows of `a` this rank owns (one GPU: all of them)
+static dim3 grid_rows(const Arr &a) { return grid2d(a.w, a.ry1 - a.ry0); }
 
 int launch_build_rhs(ifl_ctx *c) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
@@ -352,8 +354,7 @@ int launch_build_rhs(ifl_ctx *c) {
                                                                       c->fd[IFL_FIELD_V], c->hx, scale, c->bodies_d,
                                                                       c->n_bodies, c->version >= 5);
     else
-        k_build_rhs<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_U].src, c->fd[IFL_FIELD_V].src,
-                                                                scale);
+        k_build_rhs<<<grid_rows(c->r), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_U].src, c->fd[IFL_FIELD_V].src, scale);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -372,7 +373,7 @@ int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
                                                                          c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
                                                                          c->fd[IFL_FIELD_V], scale, c->version >= 5);
     else
-        k_build_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
+        k_build_matrix<<<grid_rows(c->aDiag), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -398,9 +399,9 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
         IFL_LAUNCHED(c);
         return IFL_OK;
     }
-    k_apply_pressure_u<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, scale, 1);
+    k_apply_pressure_u<<<grid_rows(u.src), 256, 0, c->stream>>>(u.src, c->p, scale, 1);
     IFL_LAUNCHED(c);
-    k_apply_pressure_v<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, scale, 1);
+    k_apply_pressure_v<<<grid_rows(v.src), 256, 0, c->stream>>>(v.src, c->p, scale, 1);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -442,7 +443,8 @@ int launch_add_inflow(ifl_ctx *c, int field, double x0, double y0, double x1, do
     const int ix1 = (int)(x1 / c->hx - f.ox);
     const int iy1 = (int)(y1 / c->hx - f.oy);
     const int xlo = imax(ix0, 0), xhi = imin(ix1, f.h); // sic: _h (v2:195)
-    const int ylo = imax(iy0, 0), yhi = imin(iy1, f.h);
+    // rows: the reference's clamp, then this rank's slab
+    const int ylo = imax(imax(iy0, 0), f.src.ry0), yhi = imin(imin(iy1, f.h), f.src.ry1);
     if (xhi <= xlo || yhi <= ylo) return IFL_OK;
     if (xhi > f.src.pitch) { // only reachable on w < h grids, where the reference itself reads out of row
         set_error("addInflow: x range [%d,%d) exceeds the row pitch on a w<h grid", xlo, xhi);

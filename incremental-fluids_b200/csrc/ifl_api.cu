@@ -48,46 +48,50 @@ void prof_end(ifl_ctx *c) {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-static int alloc_arr(Arr &a, int w, int h) {
+// All-zero array (uninitialised == zero page).  With row-slab
+// multi-GPU the rows [ry0, ry1) are this rank's; v and phi (h+1 rows) follow the cell rows
+// and the last rank takes the extra row.
+static int alloc_arr(ifl_ctx *c, Arr &a, int w, int h) {
     a.w = w;
     a.h = h;
     a.pitch = round_up(w, TILE);
     a.rows = round_up(h, TILE) + TILE;
     a.p = nullptr;
-    IFL_CUDA(cudaMalloc(&a.p, a.bytes()));
-    IFL_CUDA(cudaMemset(a.p, 0, a.bytes())); // uninitialised == zero page
-    return IFL_OK;
+    a.ry0 = c->ry0 < h ? c->ry0 : h;
+    a.ry1 = (c->rank + 1 == c->world) ? h : (c->ry1 < h ? c->ry1 : h);
+    return dist_alloc_rows(c, (void **)&a.p, a.bytes(), (size_t)a.pitch * sizeof(double), h);
 }
 
-static void free_arr(Arr &a) {
-    if (a.p) cudaFree(a.p);
+static void free_arr(ifl_ctx *c, Arr &a) {
+    if (a.p) dist_free_mem(c, a.p);
     a.p = nullptr;
 }
 
 __global__ void k_fill2d(Arr a, double value) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x < a.w && y < a.h) a.p[x + (size_t)y * a.pitch] = value;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = a.ry0 + blockIdx.y;
+    if (x < a.w && y < a.ry1) a.p[x + (size_t)y * a.pitch] = value;
 }
 
 static int fill_arr(const Arr &a, double value) {
-    k_fill2d<<<dim3((a.w + 255) / 256, a.h), 256>>>(a, value);
+    if (a.ry1 <= a.ry0) return IFL_OK;
+    k_fill2d<<<dim3((a.w + 255) / 256, a.ry1 - a.ry0), 256>>>(a, value);
     IFL_CUDA(cudaGetLastError());
     return IFL_OK;
 }
 
-static int alloc_field(Field &f, int w, int h, double ox, double oy, bool solids) {
+static int alloc_field(ifl_ctx *c, Field &f, int w, int h, double ox, double oy, bool solids) {
     f.w = w;
     f.h = h;
     f.ox = ox;
     f.oy = oy;
-    int rc = alloc_arr(f.src, w, h);
-    if (rc == IFL_OK) rc = alloc_arr(f.dst, w, h);
+    int rc = alloc_arr(c, f.src, w, h);
+    if (rc == IFL_OK) rc = alloc_arr(c, f.dst, w, h);
     if (rc != IFL_OK || !solids) return rc;
     // FluidQuantity ctor of chapters 4+ (v5:356-377): every cell fluid, volume 1
-    if ((rc = alloc_arr(f.volume, w, h)) != IFL_OK) return rc;
-    if ((rc = alloc_arr(f.normalX, w, h)) != IFL_OK) return rc;
-    if ((rc = alloc_arr(f.normalY, w, h)) != IFL_OK) return rc;
-    if ((rc = alloc_arr(f.phi, w + 1, h + 1)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(c, f.volume, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(c, f.normalX, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(c, f.normalY, w, h)) != IFL_OK) return rc;
+    if ((rc = alloc_arr(c, f.phi, w + 1, h + 1)) != IFL_OK) return rc;
     if ((rc = fill_arr(f.volume, 1.0)) != IFL_OK) return rc;
     const size_t nb = (size_t)f.src.pitch * f.src.rows;
     IFL_CUDA(cudaMalloc(&f.cell, nb));
@@ -101,9 +105,9 @@ static int alloc_field(Field &f, int w, int h, double ox, double oy, bool solids
     return IFL_OK;
 }
 
-static void free_field(Field &f) {
+static void free_field(ifl_ctx *c, Field &f) {
     Arr *arrs[] = {&f.src, &f.dst, &f.volume, &f.normalX, &f.normalY, &f.phi};
-    for (int i = 0; i < 6; i++) free_arr(*arrs[i]);
+    for (int i = 0; i < 6; i++) free_arr(c, *arrs[i]);
     if (f.cell) cudaFree(f.cell);
     if (f.body) cudaFree(f.body);
     if (f.mask) cudaFree(f.mask);
@@ -160,9 +164,13 @@ extern "C" {
 
 const char *ifl_last_error(void) { return g_err; }
 
-int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
+static int create_ctx(ifl_ctx **out, int w, int h, int version, int device, int rank, int world, const char *rendezvous) {
     if (!out || w < 2 || h < 2 || version < 1 || version > 8) {
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
+        return IFL_E_ARG;
+    }
+    if (world > 1 && version > 3) {
+        set_error("ifl_create_dist: row-slab multi-GPU covers chapters 1-3 so far (asked for chapter %d)", version);
         return IFL_E_ARG;
     }
 
@@ -186,24 +194,25 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
             rc = IFL_E_CUDA;
             break;
         }
+        if ((rc = dist_init(c, rank, world, rendezvous)) != IFL_OK) break;
         // v3:404-406: d at cell centres, u/v on the staggered faces
         const bool solids = version >= 4;
-        if ((rc = alloc_field(c->fd[IFL_FIELD_D], w, h, 0.5, 0.5, solids)) != IFL_OK) break;
-        if ((rc = alloc_field(c->fd[IFL_FIELD_U], w + 1, h, 0.0, 0.5, solids)) != IFL_OK) break;
-        if ((rc = alloc_field(c->fd[IFL_FIELD_V], w, h + 1, 0.5, 0.0, solids)) != IFL_OK) break;
+        if ((rc = alloc_field(c, c->fd[IFL_FIELD_D], w, h, 0.5, 0.5, solids)) != IFL_OK) break;
+        if ((rc = alloc_field(c, c->fd[IFL_FIELD_U], w + 1, h, 0.0, 0.5, solids)) != IFL_OK) break;
+        if ((rc = alloc_field(c, c->fd[IFL_FIELD_V], w, h + 1, 0.5, 0.0, solids)) != IFL_OK) break;
         if (version >= 6) { // temperature field at ambient temperature, v6:921-941
             c->t_amb = 294.0;
             c->g = 9.81;
-            if ((rc = alloc_field(c->fd[IFL_FIELD_T], w, h, 0.5, 0.5, true)) != IFL_OK) break;
+            if ((rc = alloc_field(c, c->fd[IFL_FIELD_T], w, h, 0.5, 0.5, true)) != IFL_OK) break;
             if ((rc = fill_arr(c->fd[IFL_FIELD_T].src, c->t_amb)) != IFL_OK) break;
         }
         if (version >= 7) {
-            if ((rc = alloc_arr(c->uDensity, w + 1, h)) != IFL_OK) break;
-            if ((rc = alloc_arr(c->vDensity, w, h + 1)) != IFL_OK) break;
+            if ((rc = alloc_arr(c, c->uDensity, w + 1, h)) != IFL_OK) break;
+            if ((rc = alloc_arr(c, c->vDensity, w, h + 1)) != IFL_OK) break;
         }
         if (solids) {
-            if ((rc = alloc_arr(c->pe, w, h)) != IFL_OK) break;
-            if ((rc = alloc_arr(c->fmask, w, h)) != IFL_OK) break;
+            if ((rc = alloc_arr(c, c->pe, w, h)) != IFL_OK) break;
+            if ((rc = alloc_arr(c, c->fmask, w, h)) != IFL_OK) break;
             if ((rc = fill_arr(c->fmask, 1.0)) != IFL_OK) break;
             if (cudaMalloc(&c->bodies_d, MAX_BODIES * sizeof(BodyDev)) != cudaSuccess ||
                 cudaMalloc(&c->ext_ready, sizeof(int)) != cudaSuccess) {
@@ -214,11 +223,18 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
         }
         Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
         const int ncells = pcg_chapter(c) ? 11 : 2; // chapters 1-2 only own _r and _p (v2:219-220)
-        for (int i = 0; i < ncells && rc == IFL_OK; i++) rc = alloc_arr(*cells[i], w, h);
+        for (int i = 0; i < ncells && rc == IFL_OK; i++) rc = alloc_arr(c, *cells[i], w, h);
         if (rc != IFL_OK) break;
-        const size_t npart = (size_t)((w + 255) / 256) * ((h + 15) / 16) + 64;
-        if (cudaMalloc(&c->partials, (npart > MAX_PARTIALS ? npart : MAX_PARTIALS) * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&c->scal, sizeof(SolveScalars)) != cudaSuccess ||
+        // two partial buffers (reductions alternate, pcg_kernels.cu); with several ranks they are
+        // rank 0's memory and every rank folds all of them
+        size_t npart = (size_t)((w + 255) / 256) * ((h + 15) / 16) + 64, pstride = 0;
+        if (npart < MAX_PARTIALS) npart = MAX_PARTIALS;
+        void *pbase = nullptr;
+        if ((rc = dist_alloc_per_rank(c, &pbase, 2 * npart * sizeof(double), &pstride)) != IFL_OK) break;
+        c->partials_buf[0] = (double *)pbase;
+        c->partials_buf[1] = c->partials_buf[0] + npart;
+        c->partials = c->partials_buf[0];
+        if (cudaMalloc(&c->scal, sizeof(SolveScalars)) != cudaSuccess ||
             cudaMemset(c->scal, 0, sizeof(SolveScalars)) != cudaSuccess ||
             cudaMallocHost(&c->scal_h, 2 * sizeof(SolveScalars)) != cudaSuccess ||
             cudaMallocHost(&c->result_h, 8 * sizeof(double)) != cudaSuccess) {
@@ -226,12 +242,15 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
             rc = IFL_E_CUDA;
             break;
         }
+        c->ddev.watchdog = &c->scal->watchdog;
         if ((rc = sweep_init(c)) != IFL_OK) break;
         if (version >= 8 && (rc = flip_init(c)) != IFL_OK) break;
         if (cudaDeviceSynchronize() != cudaSuccess) {
             set_error("ifl_create: %s", cudaGetErrorString(cudaGetLastError()));
             rc = IFL_E_CUDA;
+            break;
         }
+        rc = dist_host_barrier(c);
     } while (0);
     if (rc != IFL_OK) {
         ifl_destroy(c);
@@ -241,20 +260,33 @@ int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
     return IFL_OK;
 }
 
+int ifl_create(ifl_ctx **out, int w, int h, int version, int device) {
+    return create_ctx(out, w, h, version, device, 0, 1, nullptr);
+}
+
+int ifl_create_dist(ifl_ctx **out, int w, int h, int version, int device, int rank, int world, const char *rendezvous) {
+    if (world < 1) {
+        set_error("ifl_create_dist: world = %d", world);
+        return IFL_E_ARG;
+    }
+    return create_ctx(out, w, h, version, device, rank, world, rendezvous);
+}
+
 int ifl_destroy(ifl_ctx *c) {
     if (!c) return IFL_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 4; i++) free_field(c->fd[i]);
-    free_arr(c->pe);
-    free_arr(c->fmask);
-    free_arr(c->uDensity);
-    free_arr(c->vDensity);
+    dist_host_barrier(c); // peers may still be reading this rank's slabs
+    for (int i = 0; i < 4; i++) free_field(c, c->fd[i]);
+    free_arr(c, c->pe);
+    free_arr(c, c->fmask);
+    free_arr(c, c->uDensity);
+    free_arr(c, c->vDensity);
     if (c->bodies_d) cudaFree(c->bodies_d);
     if (c->ext_ready) cudaFree(c->ext_ready);
     Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
-    for (int i = 0; i < 11; i++) free_arr(*cells[i]);
-    if (c->partials) cudaFree(c->partials);
+    for (int i = 0; i < 11; i++) free_arr(c, *cells[i]);
+    if (c->partials_buf[0]) dist_free_mem(c, c->partials_buf[0]);
     if (c->scal) cudaFree(c->scal);
     if (c->scal_h) cudaFreeHost(c->scal_h);
     if (c->result_h) cudaFreeHost(c->result_h);
@@ -266,6 +298,7 @@ int ifl_destroy(ifl_ctx *c) {
     }
     sweep_free(c);
     flip_free(c);
+    dist_free(c);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c);
     return IFL_OK;
@@ -338,10 +371,12 @@ int ifl_upload(ifl_ctx *c, int buf, const double *host) {
         set_error("ifl_upload: bad buffer id %d", buf);
         return IFL_E_ARG;
     }
-    IFL_CUDA(cudaMemcpy2DAsync(a->p, (size_t)a->pitch * 8, host, (size_t)a->w * 8, (size_t)a->w * 8, a->h,
-                               cudaMemcpyHostToDevice, c->stream));
+    // several ranks: collective; every rank passes the whole dense array and copies its own rows
+    if (a->ry1 > a->ry0)
+        IFL_CUDA(cudaMemcpy2DAsync(a->p + (size_t)a->ry0 * a->pitch, (size_t)a->pitch * 8, host + (size_t)a->ry0 * a->w,
+                                   (size_t)a->w * 8, (size_t)a->w * 8, a->ry1 - a->ry0, cudaMemcpyHostToDevice, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));
-    return IFL_OK;
+    return dist_host_barrier(c);
 }
 
 int ifl_download(ifl_ctx *c, int buf, double *host) {
@@ -351,10 +386,13 @@ int ifl_download(ifl_ctx *c, int buf, double *host) {
         set_error("ifl_download: bad buffer id %d", buf);
         return IFL_E_ARG;
     }
+    // several ranks: collective; every rank receives the WHOLE array (the peers' slabs come over NVLink)
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    TRY(dist_host_barrier(c)); // the peers' kernels that produce their slabs have finished
     IFL_CUDA(cudaMemcpy2DAsync(host, (size_t)a->w * 8, a->p, (size_t)a->pitch * 8, (size_t)a->w * 8, a->h,
                                cudaMemcpyDeviceToHost, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));
-    return IFL_OK;
+    return dist_host_barrier(c); // nobody overwrites a slab while a peer still copies it
 }
 
 int ifl_fill(ifl_ctx *c, int buf, double value) {
@@ -365,7 +403,7 @@ int ifl_fill(ifl_ctx *c, int buf, double value) {
         return IFL_E_ARG;
     }
     if (value == 0.0 && !signbit(value)) {
-        IFL_CUDA(cudaMemsetAsync(a->p, 0, a->bytes(), c->stream));
+        IFL_CUDA(cudaMemsetAsync((char *)a->p + a->own_begin(), 0, a->own_end() - a->own_begin(), c->stream));
         return IFL_OK;
     }
     // rare path (tests): build one dense row block on the host
@@ -396,6 +434,7 @@ int ifl_quantity_add_inflow(ifl_ctx *c, int field, double x0, double y0, double 
 int ifl_advect(ifl_ctx *c, int field, double timestep) {
     CHECK_CTX(c);
     TRY(check_field(c, field));
+    TRY(dist_barrier(c));
     return launch_advect(c, field, timestep);
 }
 
@@ -676,6 +715,7 @@ static Arr *vec_arr(ifl_ctx *c, int buf) {
 
 int ifl_build_rhs(ifl_ctx *c) {
     CHECK_CTX(c);
+    TRY(dist_barrier(c));
     return launch_build_rhs(c);
 }
 
@@ -688,6 +728,7 @@ int ifl_build_pressure_matrix(ifl_ctx *c, double timestep, double density) {
 int ifl_build_preconditioner(ifl_ctx *c) {
     CHECK_CTX(c);
     TRY(need_pcg(c, "ifl_build_preconditioner"));
+    TRY(dist_barrier(c));
     return launch_mic0_factor(c);
 }
 
@@ -699,6 +740,7 @@ int ifl_apply_preconditioner(ifl_ctx *c, int dst, int a) {
         if (d == s && d) set_error("ifl_apply_preconditioner: dst and a must differ");
         return IFL_E_ARG;
     }
+    TRY(dist_barrier(c));
     TRY(launch_precon_forward(c, *d, *s, false));
     TRY(launch_precon_backward(c, *d, *s, false, false));
     IFL_CUDA(cudaMemcpyAsync(c->scal_h, c->scal, sizeof(SolveScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -718,6 +760,7 @@ int ifl_matrix_vector_product(ifl_ctx *c, int dst, int b) {
         if (d == s && d) set_error("ifl_matrix_vector_product: dst and b must differ");
         return IFL_E_ARG;
     }
+    TRY(dist_barrier(c));
     return launch_matvec(c, *d, *s, false);
 }
 
@@ -777,6 +820,7 @@ int ifl_project_gs(ifl_ctx *c, int limit, double timestep, double density, ifl_s
 
 int ifl_apply_pressure(ifl_ctx *c, double timestep, double density) {
     CHECK_CTX(c);
+    TRY(dist_barrier(c));
     return launch_apply_pressure(c, timestep, density);
 }
 
@@ -850,15 +894,21 @@ int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *info
     }
     if (c->version >= 6) return update_heat(c, timestep, infos);
     if (c->version >= 4) return update_solids(c, timestep, density, info);
+    // Row-slab multi-GPU: dist_barrier (a no-op on one GPU) sits wherever the next kernel reads
+    // rows of a neighbouring slab that the previous kernels wrote; inside the solves the
+    // reductions' folds and the sweeps' hand-off messages order the ranks.
+    TRY(dist_barrier(c)); // u, v of the previous step (advection, inflow)
     TRY(launch_build_rhs(c));
     if (pcg_chapter(c)) { // v3:433-447
         TRY(launch_build_matrix(c, timestep, density));
+        TRY(dist_barrier(c)); // aPlusX/aPlusY of the upstream slab's last row
         TRY(launch_mic0_factor(c));
         TRY(pcg_project(c, 600, info));
     } else { // v2:320-332, v1:284-297
         TRY(gs_project(c, 600, timestep, density, info));
     }
     TRY(launch_apply_pressure(c, timestep, density));
+    TRY(dist_barrier(c)); // back-traced samples of u, v, d may lie in any slab
     TRY(launch_advect(c, IFL_FIELD_D, timestep));
     TRY(launch_advect(c, IFL_FIELD_U, timestep));
     TRY(launch_advect(c, IFL_FIELD_V, timestep));
@@ -877,16 +927,17 @@ int ifl_update_host(ifl_ctx *c, double timestep, double density, double *d, doub
     }
     double *host[3] = {d, u, v};
     const int ids[3] = {IFL_FIELD_D, IFL_FIELD_U, IFL_FIELD_V};
+    // every rank moves the rows of its own slab (one GPU: everything)
     for (int i = 0; i < 3; i++) {
         Arr &a = c->fd[ids[i]].src;
-        IFL_CUDA(cudaMemcpy2DAsync(a.p, (size_t)a.pitch * 8, host[i], (size_t)a.w * 8, (size_t)a.w * 8, a.h,
-                                   cudaMemcpyHostToDevice, c->stream));
+        IFL_CUDA(cudaMemcpy2DAsync(a.p + (size_t)a.ry0 * a.pitch, (size_t)a.pitch * 8, host[i] + (size_t)a.ry0 * a.w,
+                                   (size_t)a.w * 8, (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyHostToDevice, c->stream));
     }
     TRY(ifl_update(c, timestep, density, infos));
     for (int i = 0; i < 3; i++) {
         Arr &a = c->fd[ids[i]].src;
-        IFL_CUDA(cudaMemcpy2DAsync(host[i], (size_t)a.w * 8, a.p, (size_t)a.pitch * 8, (size_t)a.w * 8, a.h,
-                                   cudaMemcpyDeviceToHost, c->stream));
+        IFL_CUDA(cudaMemcpy2DAsync(host[i] + (size_t)a.ry0 * a.w, (size_t)a.w * 8, a.p + (size_t)a.ry0 * a.pitch,
+                                   (size_t)a.pitch * 8, (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyDeviceToHost, c->stream));
     }
     IFL_CUDA(cudaStreamSynchronize(c->stream));
     return IFL_OK;

@@ -27,7 +27,16 @@ constexpr int TILE = 32;
 struct Arr {
     double *p;
     int w, h, pitch, rows;
+    // Row slab of this array that THIS rank computes: [ry0, ry1).  One GPU: [0, h).  With
+    // row-slab multi-GPU (dist.cu) `p` addresses the whole array in a virtual range shared by
+    // all ranks (each slab backed by its owner's HBM), kernels launch over the slab only and
+    // reach the neighbours' rows through NVLink peer mappings.
+    int ry0, ry1;
     __host__ __device__ size_t bytes() const { return (size_t)pitch * rows * sizeof(double); }
+    // byte range [own_begin, own_end) of the rows this rank zero-fills / copies (the last
+    // slab includes the pad rows below h)
+    __host__ __device__ size_t own_begin() const { return (size_t)ry0 * pitch * sizeof(double); }
+    __host__ __device__ size_t own_end() const { return (size_t)(ry1 == h ? rows : ry1) * pitch * sizeof(double); }
 };
 
 struct Field { // one FluidQuantity (v3:41-49; solid-body members v5:288-313)
@@ -66,6 +75,19 @@ struct SolveScalars {
 
 constexpr int MAX_PARTIALS = 8192; // per-block partial results of one reduction
 
+// ---- row-slab multi-GPU (dist.cu) ------------------------------------------------
+constexpr int MAX_WORLD = 8;
+// What a kernel needs for an in-kernel barrier across the ranks of one solver: every rank
+// owns one flag word per peer (in its own HBM, peers store into it over NVLink).
+struct DistDev {
+    int rank, world;
+    unsigned long long *epoch;                 // this rank's barrier counter (device memory)
+    unsigned long long *flags_local;           // [MAX_WORLD] written by the peers
+    unsigned long long *flags_peer[MAX_WORLD]; // flags_local of every rank (peer mappings)
+    int *watchdog;                             // SolveScalars::watchdog of this rank
+};
+struct DistState; // host side (dist.cu)
+
 } // namespace ifl
 
 struct ifl_ctx {
@@ -89,7 +111,8 @@ struct ifl_ctx {
     ifl::SolveScalars *scal_h; // pinned host mirror
     double *result_h;          // pinned 8 doubles for scalar results
     // wavefront sweep plumbing (sweep_kernels.cu)
-    unsigned long long *handoff; // [strips][pitch] x {value bits, epoch}
+    unsigned long long *handoff; // [strips][pitch] x {value bits, epoch} (this rank's array)
+    void *handoff_base;          // allocation holding every rank's hand-off array
     unsigned long long *ticket;  // strip ticket counter
     unsigned long long epoch;    // last used handoff epoch
     int n_strips;
@@ -97,6 +120,14 @@ struct ifl_ctx {
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     int sweep_v2;                      // triangular solves use sweep2_kernels.cu
+    // row-slab multi-GPU: world == 1 unless the context came from ifl_create_dist
+    int rank, world;
+    int ry0, ry1;                // cell rows [ry0, ry1) owned by this rank (multiples of 32, ry1 clipped to H)
+    ifl::DistState *dist;        // rendezvous sockets + peer mappings (null when world == 1)
+    ifl::DistDev ddev;           // device-side barrier state (world == 1: barriers are no-ops)
+    unsigned long long *handoff_down[2]; // hand-off array of the downstream rank: [0] forward sweeps, [1] backward
+    double *partials_buf[2];     // reductions alternate between two partial buffers (see pcg_kernels.cu)
+    int partials_sel;
     void *map_cache;                   // TMA tensor maps keyed by array base pointer
     unsigned long long *sweep_times_buf; // [strips][2] diagnostics buffer
     unsigned long long *sweep_times;     // == sweep_times_buf while ifl_debug_sweep_times is armed, else null
@@ -186,7 +217,61 @@ __device__ __forceinline__ double block_reduce(double v, double *red) {
 }
 #endif
 
+// ---------------------------------------------------- barrier across the ranks --
+// Called by every thread of a block with at least MAX_WORLD threads.  Rank r stores its
+// new epoch into flags_local[r] of every rank (NVLink peer stores, release at system
+// scope: everything the previous kernels of this stream wrote is visible first) and waits
+// until all its own flag words have reached that epoch.  Epochs only grow, every rank runs
+// the same sequence of barriers, so a fast rank may already be one barrier ahead.
+#ifdef __CUDACC__
+__device__ __forceinline__ void dist_barrier_block(const DistDev &d) {
+    if (d.world <= 1) return;
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = *d.epoch + 1;
+        *d.epoch = s_epoch;
+    }
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    if ((int)threadIdx.x < d.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.flags_peer[threadIdx.x] + d.rank), "l"(e) : "memory");
+        unsigned long long v = 0;
+        unsigned n = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.flags_local + threadIdx.x) : "memory");
+            if (v >= e) break;
+            if (++n > (1u << 24)) { // a peer died: raise the watchdog instead of hanging the GPU
+                *d.watchdog = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+#endif
+
+// Reductions alternate between two partial buffers: with several ranks a fast rank may
+// start the next reducing kernel while a slow one still folds the previous partials (the
+// barrier sits at the START of the fold), but it cannot get two reductions ahead.
+static inline double *partials_next(ifl_ctx *c) {
+    c->partials_sel ^= 1;
+    c->partials = c->partials_buf[c->partials_sel];
+    return c->partials;
+}
+
 // ------------------------------------------------------------ kernel entry points --
+// dist.cu
+int dist_init(ifl_ctx *c, int rank, int world, const char *rendezvous);
+void dist_free(ifl_ctx *c);
+// Array memory: cudaMalloc on one GPU; with world > 1 one virtual range mapped by all ranks.
+// rows_per_pitch describes the slab split (bytes per row); by_rank != 0 instead gives every
+// rank `bytes` of its own at [base + rank*stride) and returns the stride.
+int dist_alloc_rows(ifl_ctx *c, void **out, size_t bytes, size_t row_bytes, int h);
+int dist_alloc_per_rank(ifl_ctx *c, void **out, size_t bytes, size_t *stride);
+void dist_free_mem(ifl_ctx *c, void *p);
+int dist_barrier(ifl_ctx *c, bool gated = false); // stream-ordered barrier across the ranks (no-op when world == 1); gated: skipped once scal->done
+int dist_host_barrier(ifl_ctx *c); // host-side barrier through the rendezvous sockets
 // pcg_kernels.cu
 int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot);
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b);

@@ -27,11 +27,14 @@ constexpr int VEC_THREADS = 128;                // x-pairs per block -> 256 colu
 constexpr int VEC_COLS = VEC_THREADS * 2;
 constexpr int VEC_ROWS = 16;                    // rows walked by each thread
 
-static dim3 vec_grid(const Arr &a) { return dim3((a.w + VEC_COLS - 1) / VEC_COLS, (a.h + VEC_ROWS - 1) / VEC_ROWS); }
-static int vec_blocks(const Arr &a) {
-    dim3 g = vec_grid(a);
-    return (int)(g.x * g.y);
+// Grid over the rows [ry0, ry1) this rank owns (one GPU: the whole array).  Blocks are
+// numbered as in the whole-array grid (block row = y / VEC_ROWS; ry0 is a multiple of 32),
+// so partials land in the same slots whatever the number of ranks and vec_blocks() -- the
+// number of partials the finishing block folds -- always counts the whole array.
+static dim3 vec_grid(const Arr &a) {
+    return dim3((a.w + VEC_COLS - 1) / VEC_COLS, (a.ry1 - a.ry0 + VEC_ROWS - 1) / VEC_ROWS);
 }
+static int vec_blocks(const Arr &a) { return ((a.w + VEC_COLS - 1) / VEC_COLS) * ((a.h + VEC_ROWS - 1) / VEC_ROWS); }
 
 // Chapters 6+ mask dotProduct / scaledAdd / infinityNorm with `cell == CELL_FLUID`
 // (v6:781-826); matrixVectorProduct stays unmasked (v6:791).  `cell` is _d's byte array
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
     const int W = dst.w, H = dst.h, pitch = dst.pitch;
     const int lane = threadIdx.x & 31;
     const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
-    const int y0 = blockIdx.y * VEC_ROWS;
-    const int y1 = imin(y0 + VEC_ROWS, H);
+    const int y0 = dst.ry0 + blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, dst.ry1);
     const bool in = x < pitch; // may load (pad columns are zero)
     const double2 zero2 = make_double2(0.0, 0.0);
 
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
     }
     if (WITH_DOT) {
         const double s = block_reduce<false>(acc, red);
-        if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s;
+        if (threadIdx.x == 0) partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = s;
     }
 }
 
@@ -130,10 +133,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
     __shared__ double red[32];
     const double alpha = sc->alpha;
     const double nalpha = -alpha;
-    const int W = p.w, H = p.h, pitch = p.pitch;
+    const int W = p.w, pitch = p.pitch;
     const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
-    const int y0 = blockIdx.y * VEC_ROWS;
-    const int y1 = imin(y0 + VEC_ROWS, H);
+    const int y0 = p.ry0 + blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, p.ry1);
     double m = 0.0;
     if (x < W) {
 #pragma unroll 4
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
         }
     }
     m = block_reduce<true>(m, red);
-    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = m;
+    if (threadIdx.x == 0) partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = m;
 }
 
 // dst = a + b*scale, scale either immediate or read from the device scalars (beta)
@@ -167,10 +170,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scaled_add(Arr dst, Arr a, Arr 
         if (sc->done) return;
         scale = sc->beta;
     }
-    const int W = dst.w, H = dst.h, pitch = dst.pitch;
+    const int W = dst.w, pitch = dst.pitch;
     const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
-    const int y0 = blockIdx.y * VEC_ROWS;
-    const int y1 = imin(y0 + VEC_ROWS, H);
+    const int y0 = dst.ry0 + blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, dst.ry1);
     if (x >= W) return;
 #pragma unroll 4
     for (int y = y0; y < y1; y++) {
@@ -188,10 +191,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scaled_add(Arr dst, Arr a, Arr 
 template <bool IS_MAX>
 __global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *__restrict__ partials, CellMask mk) {
     __shared__ double red[32];
-    const int W = a.w, H = a.h, pitch = a.pitch;
+    const int W = a.w, pitch = a.pitch;
     const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
-    const int y0 = blockIdx.y * VEC_ROWS;
-    const int y1 = imin(y0 + VEC_ROWS, H);
+    const int y0 = a.ry0 + blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, a.ry1);
     double acc = 0.0;
     if (x < W) {
         for (int y = y0; y < y1; y++) {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *_
         }
     }
     acc = block_reduce<IS_MAX>(acc, red);
-    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+    if (threadIdx.x == 0) partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = acc;
 }
 
 // ---- scalar stage: one block folds the partials in a fixed order and updates the
@@ -218,14 +221,22 @@ __global__ void __launch_bounds__(VEC_THREADS) k_reduce2(Arr a, Arr b, double *_
 // 5 plain store of the reduced value to out[0].
 enum { SC_ALPHA = 0, SC_CHECK = 1, SC_BETA = 2, SC_SIGMA0 = 3, SC_CHECK0 = 4, SC_STORE = 5 };
 
+// With several ranks the partials of all slabs sit in one array (rank 0's HBM); the barrier
+// makes every rank's blocks of the preceding reducing kernel visible, then every rank folds
+// the SAME values in the SAME order: the scalars are bit-identical everywhere and equal to
+// the one-GPU run's.  (`done` is such a scalar, so the early return is taken by all ranks.)
 template <int MODE>
-__global__ void __launch_bounds__(1024) k_scalar(const double *__restrict__ partials, int n, SolveScalars *sc,
-                                                  double *out) {
+__global__ void __launch_bounds__(1024) k_scalar(const double *partials, int n, SolveScalars *sc, double *out,
+                                                  DistDev dd) {
     constexpr bool IS_MAX = (MODE == SC_CHECK || MODE == SC_CHECK0);
     if (MODE != SC_STORE && MODE != SC_SIGMA0 && MODE != SC_CHECK0 && sc->done) return;
+    dist_barrier_block(dd);
     __shared__ double red[32];
     double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) v = IS_MAX ? std_max(v, partials[i]) : (v + partials[i]);
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double pv = __ldcg(partials + i); // L2 only: the peers' blocks were written over NVLink
+        v = IS_MAX ? std_max(v, pv) : (v + pv);
+    }
     v = block_reduce<IS_MAX>(v, red);
     if (threadIdx.x != 0) return;
     if (MODE == SC_ALPHA) {
@@ -260,7 +271,7 @@ int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
     ProfScope ps_(c, IFL_K_MATVEC);
     dim3 g = vec_grid(dst);
     if (with_dot) {
-        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, c->partials, c->scal,
+        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, partials_next(c), c->scal,
                                                          mask_of(c));
         c->n_partials = vec_blocks(dst);
     } else {
@@ -273,7 +284,7 @@ int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
 
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, c->partials, mask_of(c));
+    k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, partials_next(c), mask_of(c));
     c->n_partials = vec_blocks(a);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -281,7 +292,7 @@ int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
 
 int launch_inf_norm(ifl_ctx *c, const Arr &a) {
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_reduce2<true><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, a, c->partials, mask_of(c));
+    k_reduce2<true><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, a, partials_next(c), mask_of(c));
     c->n_partials = vec_blocks(a);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -294,10 +305,11 @@ int launch_scaled_add(ifl_ctx *c, const Arr &dst, const Arr &a, const Arr &b, do
     return IFL_OK;
 }
 
-__global__ void __launch_bounds__(1024) k_store_max(const double *__restrict__ partials, int n, double *out) {
+__global__ void __launch_bounds__(1024) k_store_max(const double *partials, int n, double *out, DistDev dd) {
+    dist_barrier_block(dd);
     __shared__ double red[32];
     double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) v = std_max(v, partials[i]);
+    for (int i = threadIdx.x; i < n; i += 1024) v = std_max(v, __ldcg(partials + i));
     v = block_reduce<true>(v, red);
     if (threadIdx.x == 0) out[0] = v;
 }
@@ -306,9 +318,9 @@ __global__ void __launch_bounds__(1024) k_store_max(const double *__restrict__ p
 int launch_finish_reduce(ifl_ctx *c, bool is_max, double *out_dev) {
     ProfScope ps_(c, IFL_K_SCALAR);
     if (is_max)
-        k_store_max<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, out_dev);
+        k_store_max<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, out_dev, c->ddev);
     else
-        k_scalar<SC_STORE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, out_dev);
+        k_scalar<SC_STORE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, out_dev, c->ddev);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -316,7 +328,7 @@ int launch_finish_reduce(ifl_ctx *c, bool is_max, double *out_dev) {
 template <int MODE>
 static int scalar_stage(ifl_ctx *c) {
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_scalar<MODE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, nullptr);
+    k_scalar<MODE><<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, nullptr, c->ddev);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -333,7 +345,7 @@ static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
     {
         ProfScope ps_(c, IFL_K_AXPY2_NORM);
-        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, c->partials,
+        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, partials_next(c),
                                                                     mask_of(c));
         c->n_partials = vec_blocks(c->p);
         IFL_LAUNCHED(c);
@@ -347,18 +359,20 @@ static int enqueue_iteration(ifl_ctx *c) {
         k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
         IFL_LAUNCHED(c);
     }
-    return IFL_OK;
+    return dist_barrier(c, true); // the next matvec reads the neighbours' boundary rows of s
 }
 
 int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
     cudaStream_t st = c->stream;
     // prologue v3:350-358
     IFL_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScalars), st));
-    IFL_CUDA(cudaMemsetAsync(c->p.p, 0, c->p.bytes(), st));
+    IFL_CUDA(cudaMemsetAsync((char *)c->p.p + c->p.own_begin(), 0, c->p.own_end() - c->p.own_begin(), st));
+    IFL_TRY(dist_barrier(c, false)); // the upstream slab's last row of cy (factorisation) is final
     IFL_TRY(launch_precon_forward(c, c->z, c->r, false));
     IFL_TRY(launch_precon_backward(c, c->z, c->r, true, false));
     IFL_TRY(scalar_stage<SC_SIGMA0>(c));
-    IFL_CUDA(cudaMemcpyAsync(c->s.p, c->z.p, c->z.bytes(), cudaMemcpyDeviceToDevice, st));
+    IFL_CUDA(cudaMemcpyAsync((char *)c->s.p + c->s.own_begin(), (char *)c->z.p + c->z.own_begin(),
+                             c->z.own_end() - c->z.own_begin(), cudaMemcpyDeviceToDevice, st));
     IFL_TRY(launch_inf_norm(c, c->r));
     IFL_TRY(scalar_stage<SC_CHECK0>(c));
 

@@ -8,7 +8,8 @@
 
 namespace ifl {
 
-constexpr unsigned WATCHDOG_POLLS = 1u << 22; // hand-off polls (each an L2 round trip)
+constexpr unsigned WATCHDOG_POLLS = 1u << 23; // hand-off polls (each an L2 round trip); generous: with several ranks the
+                                              // upstream slab may start milliseconds later
 constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
 
 int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out);
@@ -105,6 +106,21 @@ __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned epoch) {
 __device__ __forceinline__ bool ll_load(const uint4 *src, unsigned epoch, double &v) {
     unsigned a, b, c, d;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+    v = __hiloint2double((int)c, (int)a);
+    return b == epoch && d == epoch;
+}
+
+// The same message across a slab boundary: the producer is another GPU storing into this
+// rank's hand-off array over NVLink, so both sides use system scope (8-byte halves stay
+// atomic on the wire, which is all the protocol needs).
+__device__ __forceinline__ void ll_store_sys(uint4 *dst, double v, unsigned epoch) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_load_sys(const uint4 *src, unsigned epoch, double &v) {
+    unsigned a, b, c, d;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
     v = __hiloint2double((int)c, (int)a);
     return b == epoch && d == epoch;
 }

@@ -82,6 +82,11 @@ struct SweepParams {
     int nst;   // ring depth
     int W, H, pitch, nbx, nby;
     uint4 *handoff; // [nby][nbx*32]
+    // row-slab multi-GPU: this launch sweeps the strips [sj_base, sj_base + nloc) of the nby
+    // strips (sweep order).  The last of them publishes into the downstream rank's hand-off
+    // array, the first polls messages that arrived over NVLink.
+    int sj_base, nloc;
+    uint4 *handoff_down;
     unsigned epoch;
     unsigned long long *ticket;
     unsigned long long ticket_base;
@@ -441,6 +446,7 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
     typedef Geo<KIND> G;
     const int nst = P.nst, nbx = P.nbx;
     const uint4 *up_row = P.handoff + (size_t)(sj - 1) * nbx * 32;
+    const bool remote = sj == P.sj_base; // the upstream strip belongs to another rank
     const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
     unsigned polls = 0;
     for (int m = 0; m < nbx; m++) {
@@ -452,7 +458,7 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
         while (published < 32) {
             if (!have) {
                 double v;
-                if (ll_load(src, P.epoch, v)) {
+                if (remote ? ll_load_sys(src, P.epoch, v) : ll_load(src, P.epoch, v)) {
                     halo_s[st * 32 + G::tcol(lane)] = v;
                     have = true;
                     polls = 0;
@@ -582,7 +588,8 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
     const int ncols = P.nbx * 32;
     int swept = (KIND == KIND_FWD) ? 4 : ((KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? 3 : 0);
     const double *last_row = smem + swept * TILE_DOUBLES + G::lane_row(31) * TP; // tile row of the strip's last row
-    uint4 *out = P.handoff + (size_t)sj * ncols;
+    const bool remote = sj + 1 == P.sj_base + P.nloc; // the downstream strip belongs to another rank
+    uint4 *out = (remote ? P.handoff_down : P.handoff) + (size_t)sj * ncols;
     const uint32_t progress_addr = smem_u32(&counters[0]);
     const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs;
     // downstream CTA's hand-off ring, hand-off counter and progress counter (same layout as ours)
@@ -618,7 +625,12 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
                     __syncwarp();
                     if (lane == 0) st_remote_u32_release(r_halo_cols, (unsigned)upto);
                 } else {
-                    if (c < upto) ll_store(out + c, row[G::tcol(c & 31)], P.epoch);
+                    if (c < upto) {
+                        if (remote)
+                            ll_store_sys(out + c, row[G::tcol(c & 31)], P.epoch);
+                        else
+                            ll_store(out + c, row[G::tcol(c & 31)], P.epoch);
+                    }
                 }
                 sent = upto;
                 if (sent == blk_end) { // all 32 columns of this block are out: the stage may drain
@@ -674,8 +686,8 @@ __global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepP
     } else {
         ticket = s_ticket;
     }
-    const int sj = ticket * P.cs + (int)rank;
-    if (sj >= P.nby) return;                 // padding CTA of the last cluster
+    const int sj = P.sj_base + ticket * P.cs + (int)rank;
+    if (sj >= P.sj_base + P.nloc) return;    // padding CTA of the last cluster
     if (P.gated && P.scal->done) return;     // the solve has converged: nothing to do
     if (threadIdx.x == 0) {
         const bool publish = sj + 1 < P.nby;
@@ -780,8 +792,17 @@ int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
 int sweep_init(ifl_ctx *c) {
     const int nbx = (c->W + 31) / 32, nby = (c->H + 31) / 32;
     c->n_strips = nby;
-    IFL_CUDA(cudaMalloc(&c->handoff, (size_t)nby * nbx * 32 * sizeof(uint4)));
-    IFL_CUDA(cudaMemset(c->handoff, 0, (size_t)nby * nbx * 32 * sizeof(uint4)));
+    {   // every rank owns a full [nby][nbx*32] hand-off array; a slab's last strip publishes into
+        // the downstream rank's array (rank+1 for forward sweeps, rank-1 for backward ones)
+        void *base = nullptr;
+        size_t stride = 0;
+        int rc = dist_alloc_per_rank(c, &base, (size_t)nby * nbx * 32 * sizeof(uint4), &stride);
+        if (rc != IFL_OK) return rc;
+        c->handoff_base = base;
+        c->handoff = (unsigned long long *)((char *)base + stride * c->rank);
+        c->handoff_down[0] = (unsigned long long *)((char *)base + stride * (c->rank + 1 < c->world ? c->rank + 1 : c->rank));
+        c->handoff_down[1] = (unsigned long long *)((char *)base + stride * (c->rank > 0 ? c->rank - 1 : c->rank));
+    }
     IFL_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned long long)));
     IFL_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned long long)));
     IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 16 * sizeof(unsigned long long)));
@@ -792,13 +813,14 @@ int sweep_init(ifl_ctx *c) {
     c->sweep_cluster = 1;
     if (const char *e = getenv("IFL_SWEEP_CLUSTER")) {
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && c->world == 1) c->sweep_cluster = v;
     }
-    // the two-columns-per-step kernels (sweep2_kernels.cu) serve the triangular solves unless
-    // IFL_SWEEP_V1=1 asks for the one-column engine of this file (kept for A/B measurements)
-    c->sweep_v2 = 1;
-    if (const char *e = getenv("IFL_SWEEP_V1"))
-        if (atoi(e) == 1) c->sweep_v2 = 0;
+    // IFL_SWEEP_V2=1 selects the two-columns-per-step kernels (sweep2_kernels.cu) for the
+    // triangular solves: bit-exact, but measured slower at 4096^2 (855 vs 702 us per sweep),
+    // so the one-column engine of this file stays the default.
+    c->sweep_v2 = 0;
+    if (const char *e = getenv("IFL_SWEEP_V2"))
+        if (atoi(e) == 1 && c->world == 1) c->sweep_v2 = 1;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -806,7 +828,8 @@ int sweep_init(ifl_ctx *c) {
 }
 
 void sweep_free(ifl_ctx *c) {
-    if (c->handoff) cudaFree(c->handoff);
+    if (c->handoff_base) dist_free_mem(c, c->handoff_base);
+    c->handoff_base = nullptr;
     if (c->ticket) cudaFree(c->ticket);
     if (c->sweep_times_buf) cudaFree(c->sweep_times_buf);
     free(c->map_cache);
@@ -849,7 +872,13 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         P.epoch = 1;
     }
     P.cs = c->sweep_cluster;
-    const int n_clusters = (P.nby + P.cs - 1) / P.cs;
+    {   // this rank's strips, in sweep order (backward sweeps start at the bottom strip)
+        const int s0 = c->ry0 / 32, s1 = (c->ry1 + 31) / 32;
+        P.nloc = s1 - s0;
+        P.sj_base = (KIND == KIND_BWD) ? P.nby - s1 : s0;
+        P.handoff_down = reinterpret_cast<uint4 *>(c->handoff_down[KIND == KIND_BWD ? 1 : 0]);
+    }
+    const int n_clusters = (P.nloc + P.cs - 1) / P.cs;
     P.ticket = c->ticket;
     P.ticket_base = c->sweep_tickets;
     c->sweep_tickets += (unsigned long long)n_clusters;
@@ -935,7 +964,7 @@ int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, boo
                               {&precon_operand(c), 1, 0, 0, nullptr},
                               {&r_for_dot, 1, 0, 0, nullptr}};
     if (with_dot) {
-        P.partials = c->partials;
+        P.partials = partials_next(c);
         c->n_partials = (c->H + 31) / 32;
         return launch_sweep<KIND_BWD, true>(c, P, spec, 5, 5);
     }
@@ -945,11 +974,12 @@ int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, boo
 // ------------------------------------------------------- Gauss-Seidel projection ----
 // project(limit, timestep) of chapters 1-2 (v2:233-277): up to `limit` lexicographic
 // sweeps over the warm-started _p, stopping when max |p - newP| < 1e-5.
-__global__ void __launch_bounds__(1024) k_scalar_gs(const double *__restrict__ partials, int n, SolveScalars *sc) {
+__global__ void __launch_bounds__(1024) k_scalar_gs(const double *partials, int n, SolveScalars *sc, DistDev dd) {
     if (sc->done) return;
+    dist_barrier_block(dd); // every rank's strips of this sweep are done; all ranks fold the same partials
     __shared__ double red[32];
     double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) v = std_max(v, partials[i]);
+    for (int i = threadIdx.x; i < n; i += 1024) v = std_max(v, __ldcg(partials + i));
     v = block_reduce<true>(v, red);
     if (threadIdx.x != 0) return;
     sc->max_error = v;
@@ -967,12 +997,12 @@ static int enqueue_gs_sweep(ifl_ctx *c, double scale) {
     P.mask_tile = -1;
     // tile 1 is p again, fetched one row further down: the old values of the row below (v2:264)
     const TileSpec spec[3] = {{&c->p, 1, 0, 1, nullptr}, {&c->p, 1, 1, 0, nullptr}, {&c->r, 1, 0, 0, nullptr}};
-    P.partials = c->partials;
+    P.partials = partials_next(c);
     c->n_partials = (c->H + 31) / 32;
     int rc = launch_sweep<KIND_GS, false>(c, P, spec, 3, 5);
     if (rc != IFL_OK) return rc;
     ProfScope ps_(c, IFL_K_SCALAR);
-    k_scalar_gs<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal);
+    k_scalar_gs<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scal, c->ddev);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }

@@ -1,0 +1,55 @@
+"""Row-slab multi-GPU: N processes, one GPU each, must reproduce the one-GPU
+run bit for bit (fields, solver status, iteration counts).  Needs >= 2 GPUs; the driver's
+single-GPU box skips it (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_dist.py`)."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_ranks(world, chapter, w, h, steps, timeout=300):
+    rdv = os.path.join(tempfile.mkdtemp(prefix="ifl_rdv_"), "sock")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), rdv, str(chapter), str(w),
+                                       str(h), str(steps)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out.decode())
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, out)
+        assert "dist ok" in out, out
+    return outs
+
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(_gpus() < 2, reason="needs >= 2 GPUs")]
+
+
+@pytest.mark.parametrize("chapter,w,h,steps", [(3, 128, 128, 3), (3, 200, 136, 2), (2, 96, 160, 2), (1, 128, 128, 2),
+                                                (3, 1024, 1024, 1)])
+def test_two_ranks_bit_identical_to_one_gpu(chapter, w, h, steps):
+    run_ranks(2, chapter, w, h, steps)
+
+
+@pytest.mark.skipif(_gpus() < 4, reason="needs >= 4 GPUs")
+def test_four_ranks(chapter=3):
+    run_ranks(4, 3, 256, 256, 2)
