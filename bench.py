@@ -19,8 +19,12 @@ cpu_baseline  the reference's own CPU code (oracle/_ref if built, else the C por
          one host core, bounded sample, extrapolated per step (stated in `sample`)
 
 --impl reference runs only the CPU reference arm and prints the same JSON line.
-N > 1: one process per GPU (torchrun), independent replicas of the same workload
-(row-slab decomposition of one grid is not built yet), barrier + max-over-ranks timing.
+N > 1: one process per GPU (torchrun), ONE grid split into row slabs (SURVEY 8e,
+csrc/dist.cu): weak scaling, the grid grows with N so that every GPU keeps 4096^2 cells
+(side = 4096*sqrt(N) rounded to whole 32-row strips: 4096, 5792, 8192, 11584); the MIC(0)
+wavefront and the stencil rows cross slab boundaries over NVLink peer mappings, the
+reductions are folded identically on every rank.  Barrier + max-over-ranks timing.
+--size S overrides the side at any N (e.g. --size 16384 for the north-star grid).
 """
 import argparse
 import importlib
@@ -139,7 +143,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = args.size
+    size = grid_side(args, args.gpus)
     cap = args.cpu_iters
     times = []
     kind = detail = None
@@ -153,18 +157,29 @@ def run_reference_arm(args):
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(size, 1),
+            "config": workload_config(size, args.gpus),
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind, "sample": detail},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def grid_side(args, n):
+    """Side of the square grid: 4096 on one GPU; with N GPUs 4096*sqrt(N) rounded to whole
+    32-row strips, i.e. a constant 4096^2 cells per GPU (weak scaling)."""
+    if args.size:
+        return args.size
+    return int(round(4096 * n ** 0.5 / 32.0)) * 32
 
 
 def workload_config(size, n):
     return {"workload": "3-conjugate-gradients smoke plume %dx%d, double, MIC(0)-PCG limit %d, dt %.3f, "
                         "inflow before every update (v3:470-486)" % (size, size, LIMIT, DT),
             "grid": [size, size], "pcg_limit": LIMIT,
-            "parallelism": "1 GPU" if n == 1 else "%d independent replicas (one grid per GPU)" % n,
-            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (17 * size * size * 8 / 1e9)}
+            "parallelism": "1 GPU" if n == 1 else
+            "%d row slabs of one %dx%d grid, one process per GPU, peer-mapped HBM over NVLink, exact MIC(0) "
+            "pipelined across slabs" % (n, size, size),
+            "cells_per_gpu": size * size // n,
+            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (17 * size * size * 8 / 1e9 / n)}
 
 
 # ------------------------------------------------------------------------- ours ----
@@ -182,8 +197,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ifl = importlib.import_module("incremental-fluids_b200")
-    size = args.size
-    s = ifl.FluidSolver(size, size, DENSITY, version=3, device=local)
+    size = grid_side(args, world)
+    rdv = "/tmp/ifl_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"))
+    s = ifl.FluidSolver(size, size, DENSITY, version=3, device=local, rank=rank, world=world, rendezvous=rdv)
     stream = torch.cuda.ExternalStream(s.stream(), device=local)
 
     def barrier():
@@ -220,19 +236,23 @@ def run_ours(args):
     s.profile(False)
 
     # ---- timed region 2: end to end through host buffers (pinned), copies included
-    host = {k: torch.empty(s.L.ifl_buf_elems(s.ctx, ifl.BUF[k + ".src"]), dtype=torch.float64).pin_memory()
-            for k in "duv"}
+    # every rank keeps the rows of its own slab in pinned host memory (one GPU: whole fields)
+    host = {k: torch.empty(s.slab_elems(k + ".src"), dtype=torch.float64).pin_memory() for k in "duv"}
     np_host = {k: v.numpy() for k, v in host.items()}
+    r0, r1 = s.rows()
     for k in "duv":
-        np_host[k][:] = s.get(k + ".src")
+        full = s.get(k + ".src")
+        w_k = size + 1 if k == "u" else size
+        np_host[k][:] = full[r0 * w_k: r0 * w_k + np_host[k].size]
+        del full
 
     def step_e2e():
         for k in "duv":
-            s._chk(s.L.ifl_upload(s.ctx, ifl.BUF[k + ".src"], np_host[k].ctypes.data))
+            s.set_slab(k + ".src", np_host[k])
         s.addInflow(*INFLOW)
         s.update(DT)
         for k in "duv":
-            s._chk(s.L.ifl_download(s.ctx, ifl.BUF[k + ".src"], np_host[k].ctypes.data))
+            s.get_slab(k + ".src", np_host[k])
 
     step_e2e()
     barrier()
@@ -255,19 +275,19 @@ def run_ours(args):
 
     if rank == 0:
         cells = size * size
-        value = cells * args.steps * world / (ms * 1e-3)
-        e2e_value = cells * args.steps * world / (ms_e2e * 1e-3)
+        value = cells * args.steps / (ms * 1e-3)  # the grid is ONE job over all ranks
+        e2e_value = cells * args.steps / (ms_e2e * 1e-3)
         peak, peak_src = measured_peak()
         shares = {k: v[0] for k, v in prof.items() if v[1] > 0}
         total_prof = sum(shares.values())
         dom = max((k for k in shares if k in ALG_BYTES), key=lambda k: shares[k])
         dom_ms, dom_n = prof[dom]
-        achieved = ALG_BYTES[dom] * cells / (dom_ms / dom_n * 1e-3) / 1e9
+        achieved = ALG_BYTES[dom] * cells / world / (dom_ms / dom_n * 1e-3) / 1e9  # per GPU (rank 0's launches)
         # whole-iteration roofline: 200 algorithmic bytes per cell per PCG iteration
         pcg_ms = sum(prof[k][0] for k in ("matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "scalar"))
         n_iter = prof["matvec"][1]
         iter_gbs = 200.0 * cells * n_iter / (pcg_ms * 1e-3) / 1e9 if n_iter else None
-        bytes_io = sum(v.numel() * 8 for v in host.values())
+        bytes_io = sum(v.numel() * 8 for v in host.values()) * world
         line = {
             "metric": "cell-updates/sec (advect+PCG project)", "value": value, "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -283,7 +303,7 @@ def run_ours(args):
                          "share_of_profiled_time": dom_ms / total_prof if total_prof else None},
             "pcg": {"iterations_per_step": iters, "iters_per_s": n_iter / (pcg_ms * 1e-3) if n_iter else None,
                     "algorithmic_gbs_200B_per_cell_iter": iter_gbs,
-                    "frac_of_peak": iter_gbs / peak if iter_gbs else None},
+                    "frac_of_peak": iter_gbs / (peak * world) if iter_gbs else None},
             "kernel_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof.items() if v[1] > 0},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -302,7 +322,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=0, help="grid side (default: 4096*sqrt(gpus), whole strips)")
     ap.add_argument("--cpu-iters", type=int, default=6, help="PCG iterations timed on the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

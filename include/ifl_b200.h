@@ -249,6 +249,16 @@ int ifl_update(ifl_ctx *ctx, double timestep, double density, ifl_solve_info *in
 int ifl_update_host(ifl_ctx *ctx, double timestep, double density, double *d, double *u, double *v,
                     ifl_solve_info *infos);
 
+/* The same with host buffers that hold only the caller's slab (ifl_slab_elems(buf) doubles,
+ * the slab's first row first): what a multi-GPU host program keeps per rank.  On one GPU
+ * the slab is the whole array and this equals ifl_update_host. */
+int ifl_update_host_slab(ifl_ctx *ctx, double timestep, double density, double *d, double *u, double *v,
+                         ifl_solve_info *infos);
+size_t ifl_slab_elems(const ifl_ctx *ctx, int buf);
+/* Slab-local ifl_upload / ifl_download (not collective; `host` = the caller's rows only). */
+int ifl_upload_slab(ifl_ctx *ctx, int buf, const double *host);
+int ifl_download_slab(ifl_ctx *ctx, int buf, double *host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,7 +52,7 @@ EXPORTS = [
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
     "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
     "ifl_project", "ifl_project_gs", "ifl_apply_pressure",
-    "ifl_add_inflow", "ifl_update", "ifl_update_host",
+    "ifl_add_inflow", "ifl_update", "ifl_update_host", "ifl_update_host_slab", "ifl_slab_elems", "ifl_upload_slab", "ifl_download_slab",
 ]
 
 
@@ -141,6 +141,11 @@ def load_library():
     L.ifl_add_inflow.argtypes = [vp, cd, cd, cd, cd, cd, cd, cd]
     L.ifl_update.argtypes = [vp, cd, cd, ctypes.POINTER(SolveInfo)]
     L.ifl_update_host.argtypes = [vp, cd, cd, vp, vp, vp, ctypes.POINTER(SolveInfo)]
+    L.ifl_update_host_slab.argtypes = [vp, cd, cd, vp, vp, vp, ctypes.POINTER(SolveInfo)]
+    L.ifl_slab_elems.restype = ctypes.c_size_t
+    L.ifl_slab_elems.argtypes = [vp, ci]
+    L.ifl_upload_slab.argtypes = [vp, ci, vp]
+    L.ifl_download_slab.argtypes = [vp, ci, vp]
     _lib = L
     return L
 
@@ -464,6 +469,23 @@ class FluidSolver:
         info = SolveInfo()
         self._chk(self.L.ifl_update_host(self.ctx, timestep, self.density, d.ctypes.data, u.ctypes.data,
                                          v.ctypes.data, ctypes.byref(info)))
+        self._record(info)
+        return self.last
+
+    def slab_elems(self, name):
+        return self.L.ifl_slab_elems(self.ctx, BUF[name])
+
+    def set_slab(self, name, arr):
+        self._chk(self.L.ifl_upload_slab(self.ctx, BUF[name], arr.ctypes.data))
+
+    def get_slab(self, name, out):
+        self._chk(self.L.ifl_download_slab(self.ctx, BUF[name], out.ctypes.data))
+
+    def update_host_slab(self, timestep, d, u, v):
+        """update() on HOST arrays holding this rank's slab rows only (in/out)."""
+        info = SolveInfo()
+        self._chk(self.L.ifl_update_host_slab(self.ctx, timestep, self.density, d.ctypes.data, u.ctypes.data,
+                                              v.ctypes.data, ctypes.byref(info)))
         self._record(info)
         return self.last
 

@@ -918,9 +918,9 @@ int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *info
     return IFL_OK;
 }
 
-int ifl_update_host(ifl_ctx *c, double timestep, double density, double *d, double *u, double *v,
-                    ifl_solve_info *infos) {
-    CHECK_CTX(c);
+// slab != 0: the host buffers hold only this rank's rows (row ry0 of each array first)
+static int update_host_impl(ifl_ctx *c, double timestep, double density, double *d, double *u, double *v,
+                            ifl_solve_info *infos, int slab) {
     if (!d || !u || !v) {
         set_error("ifl_update_host: null host buffer");
         return IFL_E_ARG;
@@ -930,17 +930,63 @@ int ifl_update_host(ifl_ctx *c, double timestep, double density, double *d, doub
     // every rank moves the rows of its own slab (one GPU: everything)
     for (int i = 0; i < 3; i++) {
         Arr &a = c->fd[ids[i]].src;
-        IFL_CUDA(cudaMemcpy2DAsync(a.p + (size_t)a.ry0 * a.pitch, (size_t)a.pitch * 8, host[i] + (size_t)a.ry0 * a.w,
-                                   (size_t)a.w * 8, (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyHostToDevice, c->stream));
+        const double *h = host[i] + (slab ? 0 : (size_t)a.ry0 * a.w);
+        IFL_CUDA(cudaMemcpy2DAsync(a.p + (size_t)a.ry0 * a.pitch, (size_t)a.pitch * 8, h, (size_t)a.w * 8,
+                                   (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyHostToDevice, c->stream));
     }
     TRY(ifl_update(c, timestep, density, infos));
     for (int i = 0; i < 3; i++) {
         Arr &a = c->fd[ids[i]].src;
-        IFL_CUDA(cudaMemcpy2DAsync(host[i] + (size_t)a.ry0 * a.w, (size_t)a.w * 8, a.p + (size_t)a.ry0 * a.pitch,
-                                   (size_t)a.pitch * 8, (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyDeviceToHost, c->stream));
+        double *h = host[i] + (slab ? 0 : (size_t)a.ry0 * a.w);
+        IFL_CUDA(cudaMemcpy2DAsync(h, (size_t)a.w * 8, a.p + (size_t)a.ry0 * a.pitch, (size_t)a.pitch * 8,
+                                   (size_t)a.w * 8, a.ry1 - a.ry0, cudaMemcpyDeviceToHost, c->stream));
     }
     IFL_CUDA(cudaStreamSynchronize(c->stream));
     return IFL_OK;
+}
+
+int ifl_update_host(ifl_ctx *c, double timestep, double density, double *d, double *u, double *v,
+                    ifl_solve_info *infos) {
+    CHECK_CTX(c);
+    return update_host_impl(c, timestep, density, d, u, v, infos, 0);
+}
+
+int ifl_update_host_slab(ifl_ctx *c, double timestep, double density, double *d, double *u, double *v,
+                         ifl_solve_info *infos) {
+    CHECK_CTX(c);
+    return update_host_impl(c, timestep, density, d, u, v, infos, 1);
+}
+
+// Slab-local transfers (not collective): `host` holds the caller's rows only.
+int ifl_upload_slab(ifl_ctx *c, int buf, const double *host) {
+    CHECK_CTX(c);
+    Arr *a = buf_arr(c, buf);
+    if (!a || !a->p || !host) {
+        set_error("ifl_upload_slab: bad buffer id %d", buf);
+        return IFL_E_ARG;
+    }
+    IFL_CUDA(cudaMemcpy2DAsync(a->p + (size_t)a->ry0 * a->pitch, (size_t)a->pitch * 8, host, (size_t)a->w * 8,
+                               (size_t)a->w * 8, a->ry1 - a->ry0, cudaMemcpyHostToDevice, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    return IFL_OK;
+}
+
+int ifl_download_slab(ifl_ctx *c, int buf, double *host) {
+    CHECK_CTX(c);
+    Arr *a = buf_arr(c, buf);
+    if (!a || !a->p || !host) {
+        set_error("ifl_download_slab: bad buffer id %d", buf);
+        return IFL_E_ARG;
+    }
+    IFL_CUDA(cudaMemcpy2DAsync(host, (size_t)a->w * 8, a->p + (size_t)a->ry0 * a->pitch, (size_t)a->pitch * 8,
+                               (size_t)a->w * 8, a->ry1 - a->ry0, cudaMemcpyDeviceToHost, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    return IFL_OK;
+}
+
+size_t ifl_slab_elems(const ifl_ctx *c, int buf) {
+    Arr *a = c ? buf_arr(const_cast<ifl_ctx *>(c), buf) : nullptr;
+    return (a && a->p) ? (size_t)a->w * (a->ry1 - a->ry0) : 0;
 }
 
 } // extern "C"
