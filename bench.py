@@ -49,6 +49,19 @@ ALG_BYTES = {"matvec": 40, "axpy2_norm": 48, "precon_fwd": 40, "precon_bwd": 48,
              "advect": 80.0 / 3, "factor": 32, "gs_sweep": 24}
 
 
+def ncu_traffic(kernel, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    ncu --set full capture (profiles/ncu_traffic.json), or None if it was taken at another size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t["grid"] == [size, size]:
+            return t["bytes_per_launch"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -298,7 +311,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(dom, size) if world == 1 else None,
+                         "algorithmic_bytes_per_launch": ALG_BYTES[dom] * cells / world, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": ALG_BYTES[dom], "mean_launch_ms": dom_ms / dom_n,
                          "share_of_profiled_time": dom_ms / total_prof if total_prof else None},
             "pcg": {"iterations_per_step": iters, "iters_per_s": n_iter / (pcg_ms * 1e-3) if n_iter else None,

@@ -168,11 +168,24 @@ struct GsConst {
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
 // logical column.  Returns the new value of the swept variable; writes results into the tile.
-template <int KIND, bool DOT, bool ALWAYS>
+// EDGE 0: interior macro-step.  EDGE 1 / 2: first / last macro-step, where lanes that have
+// not entered (have left) the strip run the same instructions on aliased operands: their
+// stores are predicated off and whatever they compute is never consumed -- a lane only
+// reads the upper lane's value of the previous step, and lane t-1 is active at step k-1
+// exactly when lane t is active at step k.  A lane's carried state is cleared at the step
+// it enters the strip (`first`); that select sits on the left-neighbour path (4 FP64 ops
+// per step), not on the shuffle path (shuffle + 3 ops) that sets the step time.
+template <int KIND, bool DOT, int EDGE>
 __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint32_t p, int c, const GsConst &gs,
-                                       bool active) {
+                                       bool active, bool first) {
+    constexpr bool ALWAYS = EDGE == 0;
     double znew;
-    const Carry old = cr;
+    if (EDGE == 1) {
+        cr.zprev = sel_f64(first, 0.0, cr.zprev);
+        cr.c1 = sel_f64(first, 0.0, cr.c1);
+        if (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) cr.c2 = sel_f64(first, 0.0, cr.c2);
+        if (KIND == KIND_GS) cr.acc = sel_f64(first, 0.0, cr.acc);
+    }
     if (KIND == KIND_GS) {
         // Missing neighbours read +0.0 (left: initial carry, up: zeroed halo row, right:
         // predicated in fetch, down: zero pad row), and `off - scale*(+0.0)` is an exact
@@ -185,7 +198,7 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         const int cnt = gs.ycnt + (c > 0 ? 1 : 0) + (c < gs.W - 1 ? 1 : 0);
         const double diag = cnt == 4 ? gs.d4 : (cnt == 3 ? gs.d3 : (cnt == 2 ? gs.d2 : gs.d1));
         znew = (o.d - off) / diag;       // v2:267
-        if (gs.yvalid && c < gs.W) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
+        if (gs.yvalid && c < gs.W && (ALWAYS || active)) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
         sts_f64_p<ALWAYS>(p, znew, active); // v2:271
     } else if (KIND == KIND_FWD) {
         double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
@@ -221,12 +234,6 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         cr.c2 = cyo;
     }
     cr.zprev = znew;
-    if (!ALWAYS) { // lanes outside the strip keep their (zero) state
-        cr.zprev = sel_f64(active, cr.zprev, old.zprev);
-        cr.c1 = sel_f64(active, cr.c1, old.c1);
-        cr.c2 = sel_f64(active, cr.c2, old.c2);
-        cr.acc = sel_f64(active, cr.acc, old.acc);
-    }
     return znew;
 }
 
@@ -268,16 +275,20 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
     // Gauss-Seidel also reads the right neighbour, i.e. looks one column further ahead
     constexpr int WAIT_KK = (KIND == KIND_GS) ? 30 : 31;
     uint32_t p = pos<KIND>(lb, 0, lane);
+    unsigned counter_seen = 0;
 #pragma unroll
     for (int kk = 0; kk < 32; kk++) {
         if (kk == WAIT_KK && wait_next) mbar_wait(full_next, parity_next, dead, scal); // lane 0 is about to touch block m+1
-        // lane 0 is about to fetch the first hand-off value of the next group of HG columns
+        // lane 0 is about to fetch the first hand-off value of the next group of HG columns.
+        // The counter is read four steps early so that its shared-memory latency is hidden;
+        // only a consumer that has caught up with its producer falls into the polling loop.
+        if (((kk + 5) % HG) == 0 && has_up && EDGE != 2 && !gs.cluster) counter_seen = lds_u32_volatile(halo_cols_addr);
         if (((kk + 1) % HG) == 0 && has_up && EDGE != 2) {
+            const unsigned need = (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols);
             if (gs.cluster)
-                wait_counter<true>(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
-            else
-                wait_counter<false>(halo_cols_addr, (unsigned)imin(32 * m + kk + 1 + HG, gs.ncols), dead, scal);
-            if (times && lane == 0 && 32 * m + kk + 1 + HG == probe) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(times[14]));
+                wait_counter<true>(halo_cols_addr, need, dead, scal);
+            else if (counter_seen < need)
+                wait_counter<false>(halo_cols_addr, need, dead, scal);
         }
         // ---- critical path first: the upper neighbour's value of the previous step
         double up = __shfl_up_sync(0xffffffffu, cr.zprev, 1);
@@ -294,12 +305,9 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         const int d0 = kk - lane;
         const bool active = (EDGE == 0) ? true : (EDGE == 1 ? d0 >= 0 : d0 < 0);
         up = sel_f64(lane == 0, ops.halo, up);
-        cell<KIND, DOT, EDGE == 0>(ops, cr, up, p, 32 * m + d0, gs, active);
+        cell<KIND, DOT, EDGE>(ops, cr, up, p, 32 * m + d0, gs, active, EDGE == 1 && d0 == 0);
         // the strip's last row (lane 31) has just completed another group of HG columns
-        if (((kk + 2) % HG) == 0) {
-            sts_u32_volatile(progress_addr, (unsigned)imax(32 * m + kk - 30, 0));
-            if (times && lane == 0 && 32 * m + kk - 30 == probe) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(times[11]));
-        }
+        if (((kk + 2) % HG) == 0) sts_u32_volatile(progress_addr, (unsigned)imax(32 * m + kk - 30, 0));
         ops = nxt;
         p = pn;
     }
@@ -657,7 +665,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
 
 // ---------------------------------------------------------------------- kernel ----
 template <int KIND, bool DOT, bool MASKED>
-__global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
     __shared__ int s_ticket;
@@ -721,7 +729,9 @@ __global__ void __launch_bounds__(160, 1) k_sweep(const __grid_constant__ SweepP
         storer_warp<KIND, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
     } else if (warp == 3) {
         if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank);
-    } else if (sj > 0 && rank == 0) {
+    } else if (warp == 5 && sj > 0 && rank == 0) {
+        // (warp 4 stays idle: it would share the compute warp's scheduler, and a spinning
+        // neighbour costs the recurrence ~12 cycles per step, profiles/microbench/step.cu)
         // first strip of a cluster: its upstream strip lives in another cluster and talks through L2
         poller_warp<KIND>(P, halo_s, sj, lane, &s_dead, s_counters);
     }
@@ -899,7 +909,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
-    cfg.blockDim = dim3(160);
+    cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
