@@ -108,7 +108,7 @@ const char *ifl_last_error(void);
  * Collective calls (every rank, same order): create/destroy, upload/download/fill, every
  * compute entry point.  ifl_download returns the WHOLE array on every rank; ifl_upload and
  * ifl_update_host move only the caller's slab rows of the (whole-array) host buffers.
- * Chapters 1-3 so far. */
+ * Chapters 1-7 (the chapter-8 particle set is not sharded yet). */
 int ifl_create_dist(ifl_ctx **out, int w, int h, int version, int device, int rank, int world, const char *rendezvous);
 /* Slab of `rank`: cell rows [row0, row1) (pure host arithmetic). */
 int ifl_dist_plan(int h, int world, int rank, int *row0, int *row1);

@@ -74,10 +74,10 @@ __device__ __forceinline__ double cerp2(const FieldView &f, double x, double y) 
 __global__ void __launch_bounds__(256) k_advect_solid(double *__restrict__ dst, int dst_pitch, FieldView self,
                                                        const uint8_t *__restrict__ cell, const uint8_t *__restrict__ body,
                                                        FieldView u, FieldView v, double timestep, double hx,
-                                                       const BodyDev *__restrict__ bodies) {
+                                                       const BodyDev *__restrict__ bodies, int ry0, int ry1) {
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= self.w || iy >= self.h) return;
+    const int iy = ry0 + blockIdx.y * 8 + (threadIdx.x >> 5); // rows [ry0, ry1): this rank's slab
+    if (ix >= self.w || iy >= ry1) return;
     if (cell[ix + (size_t)iy * self.pitch] != CELL_FLUID) return;
     double x = ix + self.ox;
     double y = iy + self.oy;
@@ -154,13 +154,12 @@ static FieldView view(const Field &f) {
 int launch_advect(ifl_ctx *c, int field, double timestep) {
     ProfScope ps_(c, IFL_K_ADVECT);
     Field &f = c->fd[field];
-    dim3 grid((f.w + 31) / 32, (f.h + 7) / 8);
     const int ry0 = f.dst.ry0, ry1 = f.dst.ry1;
     dim3 grid_own((f.w + 31) / 32, (ry1 - ry0 + 7) / 8);
     FieldView self = view(f), u = view(c->fd[IFL_FIELD_U]), v = view(c->fd[IFL_FIELD_V]);
     if (c->version >= 4)
-        k_advect_solid<<<grid, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, f.cell, f.body, u, v, timestep, c->hx,
-                                                    c->bodies_d);
+        k_advect_solid<<<grid_own, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, f.cell, f.body, u, v, timestep, c->hx,
+                                                        c->bodies_d, ry0, ry1);
     else if (c->version >= 2)
         k_advect<true><<<grid_own, 256, 0, c->stream>>>(f.dst.p, f.dst.pitch, self, u, v, timestep, c->hx, ry0, ry1);
     else

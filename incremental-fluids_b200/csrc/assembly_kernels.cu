@@ -111,9 +111,9 @@ __device__ __forceinline__ double bvy(const BodyDev &b, double x) { return (x - 
 __global__ void __launch_bounds__(256) k_build_rhs_solid(Arr r, Field d, Field u, Field v, double hx, double scale,
                                                          const BodyDev *bodies, int nb, int curved) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = r.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int w = r.w, h = r.h;
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= r.ry1) return;
     const size_t ic = x + (size_t)y * d.src.pitch;
     const size_t iu = x + (size_t)y * u.src.pitch;
     const size_t iv = x + (size_t)y * v.src.pitch;
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(256) k_build_rhs_solid(Arr r, Field d, Field u
 __global__ void __launch_bounds__(256) k_build_matrix_solid(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, Field u, Field v,
                                                             double scale, int curved) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = aDiag.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int w = aDiag.w, h = aDiag.h;
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= aDiag.ry1) return;
     const int cp = d.src.pitch;
     const size_t ic = x + (size_t)y * cp;
     double diag = 0.0, ax = 0.0, ay = 0.0;
@@ -204,9 +204,9 @@ __global__ void __launch_bounds__(256) k_apply_pressure_v_solid(Arr v, Arr p, Fi
 // collects +scale per fluid-fluid face in raster order of the scattering cell.
 __global__ void __launch_bounds__(256) k_heat_matrix(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = aDiag.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int w = aDiag.w, h = aDiag.h;
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= aDiag.ry1) return;
     const int cp = d.src.pitch;
     const size_t ic = x + (size_t)y * cp;
     double diag = 1.0, ax = 0.0, ay = 0.0;
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(256) k_heat_matrix(Arr aDiag, Arr aPlusX, Arr 
 // (that cell is earlier in raster order), then the lower cell's half.  Not masked.
 __global__ void __launch_bounds__(256) k_add_buoyancy(Arr v, Arr dsrc, Arr tsrc, double tg, double alpha, double tAmb) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = v.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = dsrc.h;
-    if (x >= v.w || y > H) return;
+    if (x >= v.w || y >= v.ry1) return;
     const size_t iv = x + (size_t)y * v.pitch;
     double val = v.p[iv];
     if (y > 0) {
@@ -259,9 +259,9 @@ __device__ __forceinline__ double cell_density(const Arr &dsrc, const Arr &tsrc,
 }
 __global__ void __launch_bounds__(256) k_density_u(Arr ud, Arr dsrc, Arr tsrc, double rhoAir, double tAmb, double alpha) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = ud.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int W = dsrc.w;
-    if (x > W || y >= ud.h) return;
+    if (x > W || y >= ud.ry1) return;
     double val = 0.0;
     if (x > 0) val += 0.5 * cell_density(dsrc, tsrc, x - 1, y, rhoAir, tAmb, alpha);
     if (x < W) val += 0.5 * cell_density(dsrc, tsrc, x, y, rhoAir, tAmb, alpha);
@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(256) k_density_u(Arr ud, Arr dsrc, Arr tsrc, d
 }
 __global__ void __launch_bounds__(256) k_density_v(Arr vd, Arr dsrc, Arr tsrc, double rhoAir, double tAmb, double alpha) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = vd.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = dsrc.h;
-    if (x >= vd.w || y > H) return;
+    if (x >= vd.w || y >= vd.ry1) return;
     double val = 0.0;
     if (y > 0) val += 0.5 * cell_density(dsrc, tsrc, x, y - 1, rhoAir, tAmb, alpha);
     if (y < H) val += 0.5 * cell_density(dsrc, tsrc, x, y, rhoAir, tAmb, alpha);
@@ -286,9 +286,9 @@ __device__ __forceinline__ double vdens_flat(const Arr &vd, int flat) { return v
 __global__ void __launch_bounds__(256) k_build_matrix_density(Arr aDiag, Arr aPlusX, Arr aPlusY, Field d, Field u,
                                                               Field v, Arr ud, Arr vd, double scale) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = aDiag.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int w = aDiag.w, h = aDiag.h;
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= aDiag.ry1) return;
     const int cp = d.src.pitch;
     const size_t ic = x + (size_t)y * cp;
     double diag = 0.0, ax = 0.0, ay = 0.0;
@@ -350,7 +350,7 @@ int launch_build_rhs(ifl_ctx *c) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = 1.0 / c->hx;
     if (c->version >= 4)
-        k_build_rhs_solid<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
+        k_build_rhs_solid<<<grid_rows(c->r), 256, 0, c->stream>>>(c->r, c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
                                                                       c->fd[IFL_FIELD_V], c->hx, scale, c->bodies_d,
                                                                       c->n_bodies, c->version >= 5);
     else
@@ -364,12 +364,12 @@ int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
     const double scale = timestep / (density * c->hx * c->hx);
     if (c->version >= 7) {
         const double scale7 = timestep / (c->hx * c->hx); // v7:681
-        k_build_matrix_density<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
+        k_build_matrix_density<<<grid_rows(c->aDiag), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
                                                                            c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
                                                                            c->fd[IFL_FIELD_V], c->uDensity, c->vDensity,
                                                                            scale7);
     } else if (c->version >= 4)
-        k_build_matrix_solid<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
+        k_build_matrix_solid<<<grid_rows(c->aDiag), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY,
                                                                          c->fd[IFL_FIELD_D], c->fd[IFL_FIELD_U],
                                                                          c->fd[IFL_FIELD_V], scale, c->version >= 5);
     else
@@ -384,18 +384,18 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
     Field &u = c->fd[IFL_FIELD_U], &v = c->fd[IFL_FIELD_V];
     if (c->version >= 7) {
         const double scale7 = timestep / c->hx; // v7:892
-        k_apply_pressure_u_density<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], c->uDensity,
+        k_apply_pressure_u_density<<<grid_rows(u.src), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], c->uDensity,
                                                                              scale7);
         IFL_LAUNCHED(c);
-        k_apply_pressure_v_density<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], c->vDensity,
+        k_apply_pressure_v_density<<<grid_rows(v.src), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], c->vDensity,
                                                                              scale7);
         IFL_LAUNCHED(c);
         return IFL_OK;
     }
     if (c->version >= 4) {
-        k_apply_pressure_u_solid<<<grid2d(u.w, u.h), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], scale);
+        k_apply_pressure_u_solid<<<grid_rows(u.src), 256, 0, c->stream>>>(u.src, c->p, c->fd[IFL_FIELD_D], scale);
         IFL_LAUNCHED(c);
-        k_apply_pressure_v_solid<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], scale);
+        k_apply_pressure_v_solid<<<grid_rows(v.src), 256, 0, c->stream>>>(v.src, c->p, c->fd[IFL_FIELD_D], scale);
         IFL_LAUNCHED(c);
         return IFL_OK;
     }
@@ -409,7 +409,7 @@ int launch_apply_pressure(ifl_ctx *c, double timestep, double density) {
 int launch_build_heat_matrix(ifl_ctx *c, double timestep) { // v6:683-712
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double scale = c->diffusion * timestep * 1.0 / (c->hx * c->hx);
-    k_heat_matrix<<<grid2d(c->W, c->H), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, c->fd[IFL_FIELD_D], scale);
+    k_heat_matrix<<<grid_rows(c->aDiag), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, c->fd[IFL_FIELD_D], scale);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -418,7 +418,7 @@ int launch_add_buoyancy(ifl_ctx *c, double timestep) { // v6:881-895
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double alpha = (c->rho_soot - c->rho_air) / c->rho_air;
     Field &v = c->fd[IFL_FIELD_V];
-    k_add_buoyancy<<<grid2d(v.w, v.h), 256, 0, c->stream>>>(v.src, c->fd[IFL_FIELD_D].src, c->fd[IFL_FIELD_T].src,
+    k_add_buoyancy<<<grid_rows(v.src), 256, 0, c->stream>>>(v.src, c->fd[IFL_FIELD_D].src, c->fd[IFL_FIELD_T].src,
                                                             timestep * c->g, alpha, c->t_amb);
     IFL_LAUNCHED(c);
     return IFL_OK;
@@ -428,9 +428,9 @@ int launch_compute_densities(ifl_ctx *c) { // v7:658-675
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const double alpha = (c->rho_soot - c->rho_air) / c->rho_air;
     Arr &ds = c->fd[IFL_FIELD_D].src, &ts = c->fd[IFL_FIELD_T].src;
-    k_density_u<<<grid2d(c->uDensity.w, c->uDensity.h), 256, 0, c->stream>>>(c->uDensity, ds, ts, c->rho_air, c->t_amb, alpha);
+    k_density_u<<<grid_rows(c->uDensity), 256, 0, c->stream>>>(c->uDensity, ds, ts, c->rho_air, c->t_amb, alpha);
     IFL_LAUNCHED(c);
-    k_density_v<<<grid2d(c->vDensity.w, c->vDensity.h), 256, 0, c->stream>>>(c->vDensity, ds, ts, c->rho_air, c->t_amb, alpha);
+    k_density_v<<<grid_rows(c->vDensity), 256, 0, c->stream>>>(c->vDensity, ds, ts, c->rho_air, c->t_amb, alpha);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }

@@ -438,6 +438,18 @@ int dist_host_barrier(ifl_ctx *c) {
     return rdv_allgather(c->dist, &one, all, 1);
 }
 
+// Sum of one integer over the ranks (host side; every rank gets the same total).
+int dist_host_sum(ifl_ctx *c, long long *v) {
+    if (c->world <= 1 || !c->dist) return IFL_OK;
+    long long all[MAX_WORLD];
+    int rc = rdv_allgather(c->dist, v, all, sizeof(long long));
+    if (rc != IFL_OK) return rc;
+    long long t = 0;
+    for (int g = 0; g < c->world; g++) t += all[g];
+    *v = t;
+    return IFL_OK;
+}
+
 // ------------------------------------------------------------------- life cycle ----
 int dist_init(ifl_ctx *c, int rank, int world, const char *rendezvous) {
     c->rank = rank;

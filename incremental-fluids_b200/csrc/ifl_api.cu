@@ -93,14 +93,11 @@ static int alloc_field(ifl_ctx *c, Field &f, int w, int h, double ox, double oy,
     if ((rc = alloc_arr(c, f.normalY, w, h)) != IFL_OK) return rc;
     if ((rc = alloc_arr(c, f.phi, w + 1, h + 1)) != IFL_OK) return rc;
     if ((rc = fill_arr(f.volume, 1.0)) != IFL_OK) return rc;
-    const size_t nb = (size_t)f.src.pitch * f.src.rows;
-    IFL_CUDA(cudaMalloc(&f.cell, nb));
-    IFL_CUDA(cudaMalloc(&f.body, nb));
-    IFL_CUDA(cudaMalloc(&f.mask, nb));
-    IFL_CUDA(cudaMemset(f.cell, 0, nb)); // CELL_FLUID
-    IFL_CUDA(cudaMemset(f.body, 0, nb));
-    IFL_CUDA(cudaMemset(f.mask, 0, nb));
-    IFL_CUDA(cudaMalloc(&f.solid_list, (size_t)w * h * sizeof(int)));
+    const size_t nb = (size_t)f.src.pitch * f.src.rows; // byte arrays share the doubles' row pitch (and slab split)
+    if ((rc = dist_alloc_rows(c, (void **)&f.cell, nb, (size_t)f.src.pitch, h)) != IFL_OK) return rc; // 0 == CELL_FLUID
+    if ((rc = dist_alloc_rows(c, (void **)&f.body, nb, (size_t)f.src.pitch, h)) != IFL_OK) return rc;
+    if ((rc = dist_alloc_rows(c, (void **)&f.mask, nb, (size_t)f.src.pitch, h)) != IFL_OK) return rc;
+    IFL_CUDA(cudaMalloc(&f.solid_list, (size_t)w * (f.src.ry1 - f.src.ry0 + 1) * sizeof(int)));
     IFL_CUDA(cudaMalloc(&f.solid_count, sizeof(int)));
     return IFL_OK;
 }
@@ -108,9 +105,9 @@ static int alloc_field(ifl_ctx *c, Field &f, int w, int h, double ox, double oy,
 static void free_field(ifl_ctx *c, Field &f) {
     Arr *arrs[] = {&f.src, &f.dst, &f.volume, &f.normalX, &f.normalY, &f.phi};
     for (int i = 0; i < 6; i++) free_arr(c, *arrs[i]);
-    if (f.cell) cudaFree(f.cell);
-    if (f.body) cudaFree(f.body);
-    if (f.mask) cudaFree(f.mask);
+    if (f.cell) dist_free_mem(c, f.cell);
+    if (f.body) dist_free_mem(c, f.body);
+    if (f.mask) dist_free_mem(c, f.mask);
     if (f.solid_list) cudaFree(f.solid_list);
     if (f.solid_count) cudaFree(f.solid_count);
     f.cell = f.body = f.mask = nullptr;
@@ -169,8 +166,8 @@ static int create_ctx(ifl_ctx **out, int w, int h, int version, int device, int 
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
         return IFL_E_ARG;
     }
-    if (world > 1 && version > 3) {
-        set_error("ifl_create_dist: row-slab multi-GPU covers chapters 1-3 so far (asked for chapter %d)", version);
+    if (world > 1 && version > 7) {
+        set_error("ifl_create_dist: row-slab multi-GPU covers chapters 1-7 (the chapter-8 particle set is not sharded yet)");
         return IFL_E_ARG;
     }
 
@@ -489,12 +486,14 @@ int ifl_fill_solid_fields(ifl_ctx *c, int field) {
     CHECK_CTX(c);
     TRY(need_solids(c, "ifl_fill_solid_fields"));
     TRY(check_field(c, field));
+    TRY(dist_barrier(c));
     return launch_fill_solid_fields(c, field);
 }
 
 int ifl_set_boundary_condition(ifl_ctx *c) {
     CHECK_CTX(c);
     TRY(need_solids(c, "ifl_set_boundary_condition"));
+    TRY(dist_barrier(c));
     return launch_set_boundary_condition(c);
 }
 
@@ -502,6 +501,7 @@ int ifl_extrapolate(ifl_ctx *c, int field) {
     CHECK_CTX(c);
     TRY(need_solids(c, "ifl_extrapolate"));
     TRY(check_field(c, field));
+    TRY(dist_barrier(c));
     return launch_extrapolate(c, field);
 }
 
@@ -528,12 +528,14 @@ double ifl_ambient_t(const ifl_ctx *c) { return c ? c->t_amb : 0.0; }
 int ifl_build_heat_matrix(ifl_ctx *c, double timestep) {
     CHECK_CTX(c);
     TRY(need_heat(c, "ifl_build_heat_matrix"));
+    TRY(dist_barrier(c));
     return launch_build_heat_matrix(c, timestep);
 }
 
 int ifl_add_buoyancy(ifl_ctx *c, double timestep) {
     CHECK_CTX(c);
     TRY(need_heat(c, "ifl_add_buoyancy"));
+    TRY(dist_barrier(c));
     return launch_add_buoyancy(c, timestep);
 }
 
@@ -543,6 +545,7 @@ int ifl_compute_densities(ifl_ctx *c) {
         set_error("ifl_compute_densities: variable density belongs to chapters 7+");
         return IFL_E_ARG;
     }
+    TRY(dist_barrier(c));
     return launch_compute_densities(c);
 }
 
@@ -671,9 +674,11 @@ int ifl_aux_download(ifl_ctx *c, int field, int which, void *host) {
     void *b;
     int w, h, p, e;
     TRY(aux_lookup(c, field, which, &b, &w, &h, &p, &e));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    TRY(dist_host_barrier(c)); // several ranks: collective, like ifl_download
     IFL_CUDA(cudaMemcpy2DAsync(host, (size_t)w * e, b, (size_t)p * e, (size_t)w * e, h, cudaMemcpyDeviceToHost, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));
-    return IFL_OK;
+    return dist_host_barrier(c);
 }
 
 int ifl_aux_upload(ifl_ctx *c, int field, int which, const void *host) {
@@ -681,6 +686,10 @@ int ifl_aux_upload(ifl_ctx *c, int field, int which, const void *host) {
     void *b;
     int w, h, p, e;
     TRY(aux_lookup(c, field, which, &b, &w, &h, &p, &e));
+    if (c->world > 1) {
+        set_error("ifl_aux_upload is a one-GPU test hook");
+        return IFL_E_ARG;
+    }
     IFL_CUDA(cudaMemcpy2DAsync(b, (size_t)p * e, host, (size_t)w * e, (size_t)w * e, h, cudaMemcpyHostToDevice, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));
     if (field == IFL_FIELD_D && which == IFL_AUX_CELL) { // keep the factorisation's fluid mask in step
@@ -722,6 +731,7 @@ int ifl_build_rhs(ifl_ctx *c) {
 int ifl_build_pressure_matrix(ifl_ctx *c, double timestep, double density) {
     CHECK_CTX(c);
     TRY(need_pcg(c, "ifl_build_pressure_matrix"));
+    TRY(dist_barrier(c));
     return launch_build_matrix(c, timestep, density);
 }
 
@@ -834,19 +844,36 @@ int ifl_add_inflow(ifl_ctx *c, double x, double y, double w, double h, double d,
 }
 
 // FluidSolver::update of chapters 4-5 (v5:927-953, v4:869-895)
+// Row-slab multi-GPU: `B` = dist_barrier, a no-op on one GPU, placed wherever the next stage
+// reads rows of a neighbouring slab that the previous stage wrote (or overwrites rows a
+// neighbour may still be reading).
+#define B TRY(dist_barrier(c))
 static int update_solids(ifl_ctx *c, double timestep, double density, ifl_solve_info *info) {
     const int fields[3] = {IFL_FIELD_D, IFL_FIELD_U, IFL_FIELD_V};
+    B;
     for (int i = 0; i < 3; i++) TRY(launch_fill_solid_fields(c, fields[i]));
+    B;
     TRY(launch_set_boundary_condition(c));
+    B;
     TRY(launch_build_rhs(c));
     TRY(launch_build_matrix(c, timestep, density));
+    B;
     TRY(launch_mic0_factor(c));
     TRY(pcg_project(c, 2000, info));
     TRY(launch_apply_pressure(c, timestep, density));
+    B;
     for (int i = 0; i < 3; i++) TRY(launch_extrapolate(c, fields[i]));
+    B;
     TRY(launch_set_boundary_condition(c));
+    B;
     for (int i = 0; i < 3; i++) TRY(launch_advect(c, fields[i], timestep));
     for (int i = 0; i < 3; i++) TRY(ifl_flip(c, fields[i]));
+    return IFL_OK;
+}
+
+static int copy_own_rows(ifl_ctx *c, const Arr &dst, const Arr &src) {
+    IFL_CUDA(cudaMemcpyAsync((char *)dst.p + dst.own_begin(), (const char *)src.p + src.own_begin(),
+                             src.own_end() - src.own_begin(), cudaMemcpyDeviceToDevice, c->stream));
     return IFL_OK;
 }
 
@@ -857,30 +884,43 @@ static int update_heat(ifl_ctx *c, double timestep, ifl_solve_info *infos) {
     const int fields[4] = {IFL_FIELD_D, IFL_FIELD_T, IFL_FIELD_U, IFL_FIELD_V};
     ifl_solve_info local[2];
     if (!infos) infos = local;
+    B;
     for (int i = 0; i < 4; i++) TRY(launch_fill_solid_fields(c, fields[i]));
     Arr &tsrc = c->fd[IFL_FIELD_T].src;
-    IFL_CUDA(cudaMemcpyAsync(c->r.p, tsrc.p, c->r.bytes(), cudaMemcpyDeviceToDevice, c->stream)); // v7:1001
+    TRY(copy_own_rows(c, c->r, tsrc)); // v7:1001
+    B;
     TRY(launch_build_heat_matrix(c, timestep));
+    B;
     TRY(launch_mic0_factor(c));
     TRY(pcg_project(c, 2000, &infos[0]));
-    IFL_CUDA(cudaMemcpyAsync(tsrc.p, c->p.p, c->p.bytes(), cudaMemcpyDeviceToDevice, c->stream)); // v7:1005
+    TRY(copy_own_rows(c, tsrc, c->p)); // v7:1005
+    B;
     TRY(launch_extrapolate(c, IFL_FIELD_T));
+    B;
     TRY(launch_add_buoyancy(c, timestep));
+    B;
     TRY(launch_set_boundary_condition(c));
+    B;
     TRY(launch_build_rhs(c));
     if (c->version >= 7) TRY(launch_compute_densities(c));
+    B;
     TRY(launch_build_matrix(c, timestep, c->rho_air));
+    B;
     TRY(launch_mic0_factor(c));
     TRY(pcg_project(c, 2000, &infos[1]));
     TRY(launch_apply_pressure(c, timestep, c->rho_air));
+    B;
     TRY(launch_extrapolate(c, IFL_FIELD_D));
     TRY(launch_extrapolate(c, IFL_FIELD_U));
     TRY(launch_extrapolate(c, IFL_FIELD_V));
+    B;
     TRY(launch_set_boundary_condition(c));
+    B;
     for (int i = 0; i < 4; i++) TRY(launch_advect(c, fields[i], timestep));
     for (int i = 0; i < 4; i++) TRY(ifl_flip(c, fields[i]));
     return IFL_OK;
 }
+#undef B
 
 int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
     CHECK_CTX(c);

@@ -272,6 +272,7 @@ int dist_alloc_per_rank(ifl_ctx *c, void **out, size_t bytes, size_t *stride);
 void dist_free_mem(ifl_ctx *c, void *p);
 int dist_barrier(ifl_ctx *c, bool gated = false); // stream-ordered barrier across the ranks (no-op when world == 1); gated: skipped once scal->done
 int dist_host_barrier(ifl_ctx *c); // host-side barrier through the rendezvous sockets
+int dist_host_sum(ifl_ctx *c, long long *v); // host-side all-reduce (sum) of one integer
 // pcg_kernels.cu
 int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot);
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b);

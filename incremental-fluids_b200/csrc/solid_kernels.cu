@@ -56,8 +56,8 @@ __device__ double occupancy(double d11, double d12, double d21, double d22) { //
 // distance field on the (w+1) x (h+1) corner grid, v5:511-520
 __global__ void __launch_bounds__(256) k_fill_phi(Arr phi, double ox, double oy, double hx, const BodyDev *bodies, int nb) {
     const int ix = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int iy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (ix >= phi.w || iy >= phi.h) return;
+    const int iy = phi.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ix >= phi.w || iy >= phi.ry1) return;
     const double x = (ix + ox - 0.5) * hx;
     const double y = (iy + oy - 0.5) * hx;
     double d = body_distance(bodies[0], x, y);
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256) k_fill_phi(Arr phi, double ox, double oy,
 __global__ void __launch_bounds__(256) k_fill_cells(Field f, double hx, const BodyDev *bodies, int nb, int curved,
                                                     double *fmask, int fmask_pitch) {
     const int ix = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int iy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (ix >= f.w || iy >= f.h) return;
+    const int iy = f.src.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ix >= f.w || iy >= f.src.ry1) return;
     const double x = (ix + f.ox) * hx;
     const double y = (iy + f.oy) * hx;
     int body = 0;
@@ -108,11 +108,13 @@ int launch_fill_solid_fields(ifl_ctx *c, int field) {
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     const int curved = c->version >= 5;
     if (curved) {
-        dim3 g((f.phi.w + 63) / 64, (f.phi.h + 3) / 4);
+        dim3 g((f.phi.w + 63) / 64, (f.phi.ry1 - f.phi.ry0 + 3) / 4);
         k_fill_phi<<<g, 256, 0, c->stream>>>(f.phi, f.ox, f.oy, c->hx, c->bodies_d, c->n_bodies);
         IFL_LAUNCHED(c);
+        int rc = dist_barrier(c); // a cell reads the corner row below it, which may be the next slab's
+        if (rc != IFL_OK) return rc;
     }
-    dim3 g((f.w + 63) / 64, (f.h + 3) / 4);
+    dim3 g((f.w + 63) / 64, (f.src.ry1 - f.src.ry0 + 3) / 4);
     const bool is_d = field == IFL_FIELD_D;
     k_fill_cells<<<g, 256, 0, c->stream>>>(f, c->hx, c->bodies_d, c->n_bodies, curved, is_d ? c->fmask.p : nullptr,
                                            c->fmask.pitch);
@@ -126,9 +128,9 @@ int launch_fill_solid_fields(ifl_ctx *c, int field) {
 // raster cell wins.  Domain wall faces are zeroed afterwards.
 __global__ void __launch_bounds__(256) k_set_bc_u(Field u, Field d, double hx, const BodyDev *bodies, int nb) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = u.src.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int W = d.w;
-    if (x > W || y >= u.h) return;
+    if (x > W || y >= u.src.ry1) return;
     const size_t iu = x + (size_t)y * u.src.pitch;
     if (x == 0 || x == W) {
         u.src.p[iu] = 0.0;
@@ -144,9 +146,9 @@ __global__ void __launch_bounds__(256) k_set_bc_u(Field u, Field d, double hx, c
 
 __global__ void __launch_bounds__(256) k_set_bc_v(Field v, Field d, double hx, const BodyDev *bodies, int nb) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int y = v.src.ry0 + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int H = d.h;
-    if (x >= v.w || y > H) return;
+    if (x >= v.w || y >= v.src.ry1) return;
     const size_t iv = x + (size_t)y * v.src.pitch;
     if (y == 0 || y == H) {
         v.src.p[iv] = 0.0;
@@ -163,9 +165,11 @@ __global__ void __launch_bounds__(256) k_set_bc_v(Field v, Field d, double hx, c
 int launch_set_boundary_condition(ifl_ctx *c) {
     Field &u = c->fd[IFL_FIELD_U], &v = c->fd[IFL_FIELD_V], &d = c->fd[IFL_FIELD_D];
     ProfScope ps_(c, IFL_K_ASSEMBLY);
-    k_set_bc_u<<<dim3((u.w + 63) / 64, (u.h + 3) / 4), 256, 0, c->stream>>>(u, d, c->hx, c->bodies_d, c->n_bodies);
+    k_set_bc_u<<<dim3((u.w + 63) / 64, (u.src.ry1 - u.src.ry0 + 3) / 4), 256, 0, c->stream>>>(u, d, c->hx, c->bodies_d,
+                                                                                            c->n_bodies);
     IFL_LAUNCHED(c);
-    k_set_bc_v<<<dim3((v.w + 63) / 64, (v.h + 3) / 4), 256, 0, c->stream>>>(v, d, c->hx, c->bodies_d, c->n_bodies);
+    k_set_bc_v<<<dim3((v.w + 63) / 64, (v.src.ry1 - v.src.ry0 + 3) / 4), 256, 0, c->stream>>>(v, d, c->hx, c->bodies_d,
+                                                                                            c->n_bodies);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
@@ -175,8 +179,8 @@ int launch_set_boundary_condition(ifl_ctx *c) {
 // cells into solid_list.  Bit 0x80 of the mask marks "already solved".
 __global__ void __launch_bounds__(256) k_ext_mask(Field f) {
     const int x = 1 + blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = 1 + blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= f.w - 1 || y >= f.h - 1) return;
+    const int y = imax(1, f.src.ry0) + blockIdx.y * 4 + (threadIdx.x >> 6); // interior rows of this rank's slab
+    if (x >= f.w - 1 || y >= imin(f.h - 1, f.src.ry1)) return;
     const int pitch = f.src.pitch;
     const int idx = x + y * pitch;
     if (f.cell[idx] == CELL_FLUID) return;
@@ -220,34 +224,52 @@ __global__ void __launch_bounds__(256) k_ext_promote(Field f, int n) {
     if ((m & 0xC0) == 0x80) f.mask[idx] = (uint8_t)(m | 0x40);
 }
 
+// Several ranks: every rank lists the interior non-fluid cells of its own slab; a round reads
+// mask / value of cells one row into the neighbouring slabs, so the ranks meet at a barrier
+// after every round and after every promotion, and the stop decision uses the number of
+// cells resolved by ALL ranks (the same dependency rounds as on one GPU, hence the same values).
 int launch_extrapolate(ifl_ctx *c, int field) {
     Field &f = c->fd[field];
     if (f.w < 3 || f.h < 3) return IFL_OK;
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     IFL_CUDA(cudaMemsetAsync(f.solid_count, 0, sizeof(int), c->stream));
-    k_ext_mask<<<dim3((f.w - 2 + 63) / 64, (f.h - 2 + 3) / 4), 256, 0, c->stream>>>(f);
-    IFL_LAUNCHED(c);
+    const int y_lo = imax(1, f.src.ry0), y_hi = imin(f.h - 1, f.src.ry1);
+    if (y_hi > y_lo) {
+        k_ext_mask<<<dim3((f.w - 2 + 63) / 64, (y_hi - y_lo + 3) / 4), 256, 0, c->stream>>>(f);
+        IFL_LAUNCHED(c);
+    }
     int n = 0;
     IFL_CUDA(cudaMemcpyAsync(&n, f.solid_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));
-    if (n == 0) return IFL_OK;
+    long long n_all = n;
+    int rc = dist_host_sum(c, &n_all);
+    if (rc != IFL_OK) return rc;
+    if (n_all == 0) return IFL_OK;
     const int blocks = (n + 255) / 256;
     // rounds in batches; stop when a whole batch resolves nothing
     const int batch = 16;
     for (int guard = 0; guard < (f.w + f.h); guard += batch) {
         IFL_CUDA(cudaMemsetAsync(c->ext_ready, 0, sizeof(int), c->stream));
         for (int r = 0; r < batch; r++) {
-            k_ext_round<<<blocks, 256, 0, c->stream>>>(f, n, c->ext_ready);
-            IFL_LAUNCHED(c);
-            k_ext_promote<<<blocks, 256, 0, c->stream>>>(f, n);
-            IFL_LAUNCHED(c);
+            if ((rc = dist_barrier(c)) != IFL_OK) return rc; // masks promoted / cells listed by the neighbours
+            if (n > 0) {
+                k_ext_round<<<blocks, 256, 0, c->stream>>>(f, n, c->ext_ready);
+                IFL_LAUNCHED(c);
+            }
+            if ((rc = dist_barrier(c)) != IFL_OK) return rc; // nobody still reads the flags promoted next
+            if (n > 0) {
+                k_ext_promote<<<blocks, 256, 0, c->stream>>>(f, n);
+                IFL_LAUNCHED(c);
+            }
         }
         int resolved = 0;
         IFL_CUDA(cudaMemcpyAsync(&resolved, c->ext_ready, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         IFL_CUDA(cudaStreamSynchronize(c->stream));
-        if (resolved == 0) break;
+        long long resolved_all = resolved;
+        if ((rc = dist_host_sum(c, &resolved_all)) != IFL_OK) return rc;
+        if (resolved_all == 0) break;
     }
-    return IFL_OK;
+    return dist_barrier(c);
 }
 
 } // namespace ifl

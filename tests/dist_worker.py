@@ -4,6 +4,7 @@ Runs the plume on `world` GPUs through the C ABI, then the same plume on ONE GPU
 rank's), and demands bit-identical fields, solver status and iteration counts; rank 0 also
 checks against the CPU oracle (<= 1e-10, equal iteration counts) at sizes it finishes fast."""
 import importlib
+import math
 import os
 import sys
 
@@ -14,24 +15,46 @@ sys.path.insert(0, ROOT)
 ifl = importlib.import_module("incremental-fluids_b200")
 
 
+def make_solver(chapter, w, h, **kw):
+    """The chapter's shipped plume: chapters 4+ with a rotating box and a sphere (the solver
+    holds the list by reference, the caller moves the bodies; v5:986-1011), chapters 6-7 with
+    the heat / variable-density constructor (v7:1091-1099)."""
+    bodies = None
+    if chapter >= 4:
+        bodies = [ifl.SolidBox(0.5, 0.6, 0.7, 0.1, math.pi * 0.25, 0.0, 0.0, 0.3),
+                  ifl.SolidSphere(0.3, 0.25, 0.12, 0.0, 0.0, 0.0, 0.0)]
+    if chapter >= 6:
+        return ifl.FluidSolver(w, h, 0.1, version=chapter, bodies=bodies, rho_soot=1.0 if chapter == 7 else 0.1,
+                               diffusion=0.01, **kw)
+    return ifl.FluidSolver(w, h, 0.1, version=chapter, bodies=bodies, **kw)
+
+
 def plume(solver, steps, chapter):
     infos = []
-    for _ in range(steps):
-        solver.addInflow(0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)
+    for i in range(steps):
+        if chapter >= 6:
+            solver.addInflow(0.45, 0.2, 0.15, 0.03, 1.0, solver.ambientT() + 300.0, 0.0, 0.0)  # v6:1086
+        else:
+            solver.addInflow(0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)
         infos.append(solver.update(0.005))
+        if chapter >= 6:
+            infos.append(solver.last_heat)
+        if chapter >= 4:
+            for b in solver.bodies:
+                b.update(0.005)
     return infos
 
 
 def main():
     rdv, chapter, w, h, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    multi = ifl.FluidSolver(w, h, 0.1, version=chapter, device=rank, rank=rank, world=world, rendezvous=rdv)
+    multi = make_solver(chapter, w, h, device=rank, rank=rank, world=world, rendezvous=rdv)
     r0, r1 = multi.rows()
     assert r0 % 32 == 0 and r0 < r1 <= h, (r0, r1)
     rng = np.random.default_rng(7)
     rvec = rng.uniform(-1, 1, w * h)
     gran = {}
-    if chapter >= 3:  # granular hot-path ops across the slab boundary
+    if chapter == 3:  # granular hot-path ops across the slab boundary
         multi.buildPressureMatrix(0.005)
         multi.buildPreconditioner()
         multi.set("r", rvec)
@@ -41,13 +64,13 @@ def main():
                 "dot": multi.dotProduct("z", "r"), "norm": multi.infinityNorm("s")}
         multi.set("r", np.zeros(w * h))
     infos_m = plume(multi, steps, chapter)
-    names = ["d.src", "u.src", "v.src", "p"]
+    names = ["d.src", "u.src", "v.src", "p"] + (["t.src"] if chapter >= 6 else [])
     got = {k: multi.get(k) for k in names}
     launches = multi.launches()
     multi.barrier()
 
-    single = ifl.FluidSolver(w, h, 0.1, version=chapter, device=rank)
-    if chapter >= 3:
+    single = make_solver(chapter, w, h, device=rank)
+    if chapter == 3:
         single.buildPressureMatrix(0.005)
         single.buildPreconditioner()
         single.set("r", rvec)
@@ -66,7 +89,7 @@ def main():
             rank, k, float(np.max(np.abs(a - b))))
     single.close()
 
-    if rank == 0 and w * h <= 512 * 512:
+    if rank == 0 and w * h <= 512 * 512 and chapter <= 3:
         from oracle import portapi
         ora = portapi.PortSolver(chapter, w, h, 0.1)
         infos_o = [None] * steps

@@ -50,6 +50,15 @@ def test_two_ranks_bit_identical_to_one_gpu(chapter, w, h, steps):
     run_ranks(2, chapter, w, h, steps)
 
 
+@pytest.mark.parametrize("chapter,w,h,steps", [(4, 128, 128, 2), (5, 160, 128, 3), (6, 128, 160, 2), (7, 160, 128, 2)])
+def test_two_ranks_solids_heat_density(chapter, w, h, steps):
+    """Chapters 4-7: bodies (moving), fractional volumes, extrapolation, heat solve, variable
+    density -- two slabs must reproduce the one-GPU fields bit for bit.  (Chapter 7 needs
+    h <= w + 1: the reference indexes _vDensity with _u's row stride, v7:694, and reads past
+    the array on taller grids.)"""
+    run_ranks(2, chapter, w, h, steps)
+
+
 @pytest.mark.skipif(_gpus() < 4, reason="needs >= 4 GPUs")
 def test_four_ranks(chapter=3):
     run_ranks(4, 3, 256, 256, 2)
