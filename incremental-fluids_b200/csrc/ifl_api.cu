@@ -166,6 +166,13 @@ static int create_ctx(ifl_ctx **out, int w, int h, int version, int device, int 
         set_error("ifl_create: bad argument (w=%d h=%d version=%d)", w, h, version);
         return IFL_E_ARG;
     }
+    if (version == 7 && h > w + 1) {
+        // v7:694/700 index _vDensity (w columns per row) with _u's row stride w+1: on grids taller
+        // than w+1 the reference itself reads past the end of the array (undefined behaviour),
+        // so there is nothing to be bit-exact with.
+        set_error("ifl_create: chapter 7 needs h <= w + 1 (the reference reads _vDensity out of bounds on taller grids)");
+        return IFL_E_ARG;
+    }
     if (world > 1 && version > 7) {
         set_error("ifl_create_dist: row-slab multi-GPU covers chapters 1-7 (the chapter-8 particle set is not sharded yet)");
         return IFL_E_ARG;

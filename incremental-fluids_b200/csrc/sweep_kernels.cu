@@ -348,15 +348,18 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
     // operands of the very first step (lane 0: column 0; the others idle on column 0)
+    // Everything that does not depend on the upstream strip happens BEFORE the wait for its
+    // first hand-off group: that wait sits on the critical path of the whole sweep.
     mbar_wait(&full[0], 0, dead, P.scal);
+    fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
+    if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     if (has_up) {
         if (P.cs > 1)
             wait_counter<true>(halo_cols_addr, HG, dead, P.scal);
         else
             wait_counter<false>(halo_cols_addr, HG, dead, P.scal);
+        ops.halo = lds_f64(halo0);
     }
-    fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
-    if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
     unsigned par_next = 0;                        // parity of full[sn] for block m+1
     const int probe = (nbx / 2) * 32; // diagnostics: hand-off timestamps for the group ending at this column

@@ -175,6 +175,100 @@ static void run(const char *name, double *out, long long *cyc, unsigned *spin, i
     printf("  \"%s\": %.1f,\n", name, (double)c / (nmacro * 32));
 }
 
+// Two interleaved sub-strips in ONE warp (rows 0..31 and 32..63 of a 64-row strip): the
+// second recurrence is independent of the first within a step (it consumes what the first
+// produced 33 steps earlier, through a shared-memory ring), so its instructions fill the
+// issue slots the first chain leaves empty.
+constexpr int NST2 = 3;
+template <int F>
+__global__ void __launch_bounds__(192, 1) k_step2(double *out, long long *cyc, int nmacro, int slot) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ unsigned counters[4];
+    __shared__ double ring[128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *sm = reinterpret_cast<double *>(smem);
+    for (int i = threadIdx.x; i < 2 * NST2 * 4 * 33 * 32; i += blockDim.x) sm[i] = 1e-3 * ((i * 7) % 13);
+    if (threadIdx.x < 128) ring[threadIdx.x] = 0.25;
+    if (threadIdx.x == 0) {
+        counters[0] = 0; counters[1] = 1u << 30; counters[2] = 0; counters[3] = 1u << 30;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+    }
+    __syncthreads();
+    if (warp == 3 && (F & F_IDLE)) { for (int i = 0; i < 40; i++) __nanosleep(1000000); return; }
+    if (warp != 0) return;
+    constexpr int T4 = 4 * TILE_BYTES;
+    const uint32_t baseA = smem_u32(smem) + (uint32_t)((1 + lane) * 256);
+    const uint32_t baseB = baseA + NST2 * T4;
+    const uint32_t halo0 = smem_u32(ring);
+    const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
+    double zA = 0.5 + lane * 1e-3, c1A = 1e-3, zB = 0.4 + lane * 1e-3, c1B = 1e-3;
+    double aA = 1.0, cxA = 1e-3, cyA = 2e-3, prA = 0.999, hA = 0.25;
+    double aB = 1.0, cxB = 1e-3, cyB = 2e-3, prB = 0.999, hB = 0.25;
+    const long long t0 = clock64();
+    for (int m = 0; m < nmacro; m++) {
+        const uint32_t sA = baseA + (uint32_t)((m % NST2) * T4) - (uint32_t)(8 * lane);
+        const uint32_t sA2 = baseA + (uint32_t)(((m + NST2 - 1) % NST2) * T4) + 256u - (uint32_t)(8 * lane);
+        const uint32_t sB = baseB + (uint32_t)((m % NST2) * T4) - (uint32_t)(8 * lane);
+        const uint32_t sB2 = baseB + (uint32_t)(((m + NST2 - 1) % NST2) * T4) + 256u - (uint32_t)(8 * lane);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk++) {
+            if ((F & F_SYNC) && ((kk + 1) % 8) == 0) {
+                unsigned n = 0;
+                while (lds_u32_volatile(halo_cols_addr) < (unsigned)(32 * m + kk + 9) && ++n < 1000) {}
+            }
+            double upA = __shfl_up_sync(0xffffffffu, zA, 1);
+            double upB = __shfl_up_sync(0xffffffffu, zB, 1);
+            const uint32_t bA = (lane > kk + 1) ? sA2 : sA, bB = (lane > kk + 1) ? sB2 : sB;
+            const uint32_t pA = bA + (uint32_t)(8 * (kk + 1)), pB = bB + (uint32_t)(8 * (kk + 1));
+            const double naA = lds_f64(pA), ncxA = lds_f64(pA + TILE_BYTES), ncyA = lds_f64(pA + 2 * TILE_BYTES - 256), nprA = lds_f64(pA + 3 * TILE_BYTES);
+            const double naB = lds_f64(pB), ncxB = lds_f64(pB + TILE_BYTES), ncyB = lds_f64(pB + 2 * TILE_BYTES - 256), nprB = lds_f64(pB + 3 * TILE_BYTES);
+            const double nhA = lds_f64(halo0 + (uint32_t)(8 * ((kk + 1) & 31)) + 512);
+            const double nhB = lds_f64(halo0 + (uint32_t)(8 * ((kk + 1) & 31)));   // what sub-strip A's last row wrote 33 steps ago
+            upA = sel_f64(lane == 0, hA, upA);
+            upB = sel_f64(lane == 0, hB, upB);
+            double tA = aA - c1A * zA; tA = tA - cyA * upA; zA = tA * prA; c1A = cxA;
+            double tB = aB - c1B * zB; tB = tB - cyB * upB; zB = tB * prB; c1B = cxB;
+            const uint32_t qA = ((lane > kk) ? sA2 : sA) + (uint32_t)(8 * kk), qB = ((lane > kk) ? sB2 : sB) + (uint32_t)(8 * kk);
+            sts_f64(qA, zA);
+            sts_f64(qB, zB);
+            if (lane == 31) sts_f64(halo0 + (uint32_t)(8 * ((kk + 1) & 31)), zA); // A's last row feeds B's first
+            if ((F & F_SYNC) && ((kk + 2) % 8) == 0) sts_u32_volatile(progress_addr, (unsigned)(32 * m + kk));
+            aA = naA; cxA = ncxA; cyA = ncyA; prA = nprA; hA = nhA;
+            aB = naB; cxB = ncxB; cyB = ncyB; prB = nprB; hB = nhB;
+        }
+        if (F & F_MBAR) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+            unsigned ok = 0, n = 0;
+            while (!ok && ++n < 1000) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar[0])), "r"((unsigned)(m & 1)) : "memory");
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) cyc[slot] = t1 - t0;
+    out[lane] = zA + c1A + zB + c1B;
+}
+
+template <int F>
+static void run2(const char *name, double *out, long long *cyc, int slot) {
+    const int nmacro = 128;
+    const size_t smem = (size_t)2 * NST2 * 4 * TILE_BYTES;
+    cudaFuncSetAttribute(k_step2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; rep++) {
+        k_step2<F><<<1, 192, smem>>>(out, cyc, nmacro, slot);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+    }
+    long long c;
+    cudaMemcpy(&c, cyc + slot, 8, cudaMemcpyDeviceToHost);
+    printf("  \"%s\": %.1f,\n", name, (double)c / (nmacro * 32));
+}
+
 int main() {
     double *out; long long *cyc; unsigned *spin;
     cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 1024); cudaMalloc(&spin, 4);
@@ -203,6 +297,9 @@ int main() {
     run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SYNC | F_MBAR | F_IDLE, 8>("plus_sync_mbar_unroll8_idle_warp", out, cyc, spin, 23);
     run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SYNC | F_MBAR | F_IDLE, 16>("plus_sync_mbar_unroll16_idle_warp", out, cyc, spin, 24);
     run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SYNC | F_MBAR | F_STORER | F_PUB, 8>("plus_sync_mbar_unroll8_storer_publisher", out, cyc, spin, 25);
+    run2<0>("two_substrips_core", out, cyc, 30);
+    run2<F_IDLE>("two_substrips_core_idle_warp", out, cyc, 31);
+    run2<F_SYNC | F_MBAR | F_IDLE>("two_substrips_sync_mbar_idle_warp", out, cyc, 32);
     run<F_SHFL | F_LDS | F_STS>("shfl_lds_sts_nosel", out, cyc, spin, 9);
     run<F_LDS | F_STS>("lds_sts_noshfl", out, cyc, spin, 10);
     printf("  \"unit\": \"SM cycles per step\"\n}\n");
