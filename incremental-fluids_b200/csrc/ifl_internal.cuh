@@ -120,6 +120,7 @@ struct ifl_ctx {
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     int sweep_v2;                      // triangular solves use sweep2_kernels.cu
+    int sweep_v3;                      // triangular solves use sweep3_kernels.cu (one-warp CTAs, chapters 1-3)
     // row-slab multi-GPU: world == 1 unless the context came from ifl_create_dist
     int rank, world;
     int ry0, ry1;                // cell rows [ry0, ry1) owned by this rank (multiples of 32, ry1 clipped to H)
@@ -290,6 +291,9 @@ int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve
 // sweep2_kernels.cu
 int launch_precon_forward2(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
 int launch_precon_backward2(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
+// sweep3_kernels.cu
+int launch_precon_forward3(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
+int launch_precon_backward3(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 // solid_kernels.cu (chapters 4+)
 int launch_fill_solid_fields(ifl_ctx *c, int field);
 int launch_set_boundary_condition(ifl_ctx *c);

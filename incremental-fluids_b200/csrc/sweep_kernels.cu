@@ -802,6 +802,42 @@ int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
     return IFL_OK;
 }
 
+// Store map of one pitched cell array for the one-warp engine (sweep3_kernels.cu): 32 x 32
+// boxes; the global extent is the LOGICAL w x h, so the hardware clips pad columns / rows.
+int sweep_get_store_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
+    MapCache *mc = (MapCache *)c->map_cache;
+    for (int i = 0; i < mc->n; i++)
+        if (mc->key[i] == a.p && mc->box_w[i] == -32) {
+            *out = mc->map[i];
+            return IFL_OK;
+        }
+    PFN_encodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return IFL_E_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.w, (cuuint64_t)a.h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.pitch * sizeof(double)};
+    const cuuint32_t box[2] = {32u, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.p, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (store map) failed (%d) for a %dx%d array", (int)r, a.w, a.h);
+        return IFL_E_CUDA;
+    }
+    if (mc->n < MapCache::N) {
+        mc->key[mc->n] = a.p;
+        mc->box_w[mc->n] = -32;
+        mc->map[mc->n] = m;
+        mc->n++;
+    }
+    *out = m;
+    return IFL_OK;
+}
+
 int sweep_init(ifl_ctx *c) {
     const int nbx = (c->W + 31) / 32, nby = (c->H + 31) / 32;
     c->n_strips = nby;
@@ -834,6 +870,13 @@ int sweep_init(ifl_ctx *c) {
     c->sweep_v2 = 0;
     if (const char *e = getenv("IFL_SWEEP_V2"))
         if (atoi(e) == 1 && c->world == 1) c->sweep_v2 = 1;
+    // IFL_SWEEP_V3=1 selects the one-warp-per-CTA engine (sweep3_kernels.cu) for the triangular
+    // solves of chapters 1-3: bit-exact, predicted 77 cycles per step by the microbenchmark but
+    // measured 100 (688 us per 4096^2 sweep against 645 us here) once real TMA traffic shares the
+    // shared-memory pipe with the shuffles; kept for A/B measurements.
+    c->sweep_v3 = 0;
+    if (const char *e = getenv("IFL_SWEEP_V3"))
+        if (atoi(e) == 1 && c->version <= 3 && c->sweep_cluster == 1 && !c->sweep_v2) c->sweep_v3 = 1;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -952,6 +995,7 @@ int launch_mic0_factor(ifl_ctx *c) {
 static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
+    if (c->sweep_v3) return launch_precon_forward3(c, dst, a, gated);
     if (c->sweep_v2) return launch_precon_forward2(c, dst, a, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
@@ -966,6 +1010,7 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
+    if (c->sweep_v3) return launch_precon_backward3(c, dst, r_for_dot, with_dot, gated);
     if (c->sweep_v2) return launch_precon_backward2(c, dst, r_for_dot, with_dot, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);

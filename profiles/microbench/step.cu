@@ -14,7 +14,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum { F_SHFL = 1, F_SEL = 2, F_LDS = 4, F_STS = 8, F_ADDR = 16, F_SYNC = 32, F_MBAR = 64, F_SPIN = 128, F_TWO = 256, F_PUB = 512, F_STORER = 1024, F_PUBSLEEP = 2048, F_IDLE = 4096, F_ALU = 8192 };
+enum { F_SHFL = 1, F_SEL = 2, F_LDS = 4, F_STS = 8, F_ADDR = 16, F_SYNC = 32, F_MBAR = 64, F_SPIN = 128, F_TWO = 256, F_PUB = 512, F_STORER = 1024, F_PUBSLEEP = 2048, F_IDLE = 4096, F_ALU = 8192, F_SELF = 16384, F_DOT = 32768 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double lds_f64(uint32_t a) {
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(160, 1) k_step(double *out, long long *cyc, in
     const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
     double z = 0.5 + lane * 1e-3, c1 = 1e-3;
     double a = 1.0, cx = 1e-3, cy = 2e-3, pr = 0.999, halo = 0.25;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    double dot = 0.0;
     const long long t0 = clock64();
     for (int m = 0; m < nmacro; m++) {
         const uint32_t sA = base0 + (uint32_t)((m % NST) * NT * TILE_BYTES) - (uint32_t)(8 * lane);
@@ -116,6 +118,31 @@ __global__ void __launch_bounds__(160, 1) k_step(double *out, long long *cyc, in
             if ((F & F_SYNC) && ((ku + 1) % 8) == 0) {
                 unsigned n = 0;
                 while (lds_u32_volatile(halo_cols_addr) < (unsigned)(32 * m + kk + 9) && ++n < 1000) {}
+            }
+            if ((F & F_SELF) && (kk % 8) == 0) {
+                // the compute warp is its own publisher and poller: every 8 steps lanes 0..7 send the
+                // 8 columns the last row has just finished as LL messages and pick up the 8 messages
+                // they asked for 8 steps ago (validated by epoch, spun on only if missing)
+                uint4 *llo = reinterpret_cast<uint4 *>(out + 8192) + ((32 * m + kk) & 1023);
+                const uint4 *lli = reinterpret_cast<const uint4 *>(out + 65536) + ((32 * m + kk) & 1023);
+                if (lane < 8) {
+                    const double v = lds_f64(base0 - (uint32_t)((1 + lane) * 256) + 32 * 256 + 4 * TILE_BYTES + (uint32_t)(8 * ((kk + lane) & 31)));
+                    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+                    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(llo + lane), "r"(lo), "r"(1u), "r"(hi), "r"(1u) : "memory");
+                }
+                // consume the prefetched messages
+                bool ok = lane >= 8 || (pre.y == 0u && pre.w == 0u);
+                unsigned nn = 0;
+                while (!__all_sync(0xffffffffu, ok) && ++nn < 100) {
+                    if (!ok) {
+                        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre.x), "=r"(pre.y), "=r"(pre.z), "=r"(pre.w) : "l"(lli + lane) : "memory");
+                        ok = pre.y == 0u && pre.w == 0u;
+                    }
+                }
+                if (lane < 8) sts_f64(halo0 + (uint32_t)(8 * ((kk + 8 + lane) & 31)), __hiloint2double((int)pre.z, (int)pre.x));
+                // ask for the next group
+                if (lane < 8)
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre.x), "=r"(pre.y), "=r"(pre.z), "=r"(pre.w) : "l"(lli + 8 + lane) : "memory");
             }
             double up = (F & F_SHFL) ? __shfl_up_sync(0xffffffffu, z, 1) : z;
             // operands of the next step
@@ -135,6 +162,7 @@ __global__ void __launch_bounds__(160, 1) k_step(double *out, long long *cyc, in
             t = t - cy * up;
             z = t * pr;
             c1 = cx;
+            if (F & F_DOT) dot += z * nh; // z.r folded by the compute warp itself (one more operand per step)
             if (F & F_STS) {
                 uint32_t b = sA;
                 if (F & F_ADDR) b = (lane > kk) ? sB : sA;
@@ -156,7 +184,7 @@ __global__ void __launch_bounds__(160, 1) k_step(double *out, long long *cyc, in
     }
     const long long t1 = clock64();
     if (lane == 0) cyc[slot] = t1 - t0;
-    out[lane] = z + c1;
+    out[lane] = z + c1 + dot;
 }
 
 template <int F, int U = 32>
@@ -271,7 +299,7 @@ static void run2(const char *name, double *out, long long *cyc, int slot) {
 
 int main() {
     double *out; long long *cyc; unsigned *spin;
-    cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 1024); cudaMalloc(&spin, 4);
+    cudaMalloc(&out, 1 << 20); cudaMemset(out, 0, 1 << 20); cudaMalloc(&cyc, 1024); cudaMalloc(&spin, 4);
     printf("{\n");
     run<0>("chain_3op_register", out, cyc, spin, 0);
     run<F_SHFL>("shfl", out, cyc, spin, 1);
@@ -300,6 +328,9 @@ int main() {
     run2<0>("two_substrips_core", out, cyc, 30);
     run2<F_IDLE>("two_substrips_core_idle_warp", out, cyc, 31);
     run2<F_SYNC | F_MBAR | F_IDLE>("two_substrips_sync_mbar_idle_warp", out, cyc, 32);
+    run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SELF>("single_warp_self_publish_poll", out, cyc, spin, 40);
+    run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SELF | F_MBAR>("single_warp_self_publish_poll_mbar", out, cyc, spin, 41);
+    run<F_SHFL | F_SEL | F_LDS | F_STS | F_ADDR | F_SELF | F_MBAR | F_DOT>("single_warp_self_publish_poll_mbar_dot", out, cyc, spin, 42);
     run<F_SHFL | F_LDS | F_STS>("shfl_lds_sts_nosel", out, cyc, spin, 9);
     run<F_LDS | F_STS>("lds_sts_noshfl", out, cyc, spin, 10);
     printf("  \"unit\": \"SM cycles per step\"\n}\n");
