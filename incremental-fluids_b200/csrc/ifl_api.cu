@@ -144,12 +144,17 @@ static bool pcg_chapter(const ifl_ctx *c) { return c->version >= 3; }
 
 using namespace ifl;
 
-#define CHECK_CTX(c)                       \
-    do {                                   \
-        if (!(c)) {                        \
-            set_error("null context");     \
-            return IFL_E_ARG;              \
-        }                                  \
+// every entry point runs on the context's device (a process may hold contexts on several GPUs)
+#define CHECK_CTX(c)                                   \
+    do {                                               \
+        if (!(c)) {                                    \
+            set_error("null context");                 \
+            return IFL_E_ARG;                          \
+        }                                              \
+        if (cudaSetDevice((c)->device) != cudaSuccess) { \
+            set_error("cudaSetDevice(%d) failed", (c)->device); \
+            return IFL_E_CUDA;                         \
+        }                                              \
     } while (0)
 #define TRY(expr)                          \
     do {                                   \

@@ -77,6 +77,7 @@ constexpr int MAX_PARTIALS = 8192; // per-block partial results of one reduction
 
 // ---- row-slab multi-GPU (dist.cu) ------------------------------------------------
 constexpr int MAX_WORLD = 8;
+#define IFL_MAX_DEVICES 64
 // What a kernel needs for an in-kernel barrier across the ranks of one solver: every rank
 // owns one flag word per peer (in its own HBM, peers store into it over NVLink).
 struct DistDev {

@@ -486,10 +486,10 @@ static int launch2(ifl_ctx *c, const Arr &swept_in, const Arr &swept_out, const 
     if (DOT) c->n_partials = P.nby;
     const size_t smem = (size_t)NST * STAGE_B + RING_COLS * sizeof(double);
     auto kern = masked ? k_sweep2<BWD, DOT, true> : k_sweep2<BWD, DOT, false>;
-    static bool attr_set[2][2][2];
-    if (!attr_set[BWD][DOT][masked]) {
+    static bool attr_set[IFL_MAX_DEVICES][2][2][2]; // function attributes are per device
+    if (!attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked]) {
         IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[BWD][DOT][masked] = true;
+        attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked] = true;
     }
     ProfScope ps_(c, BWD ? IFL_K_PRECON_BWD : IFL_K_PRECON_FWD);
     kern<<<P.nby, 160, smem, c->stream>>>(P);

@@ -371,10 +371,10 @@ static int launch3(ifl_ctx *c, const Arr &swept_in, const Arr &swept_out, const 
     }
     P.times = c->sweep_times;
     const size_t smem = (size_t)NST * P.nt * TILE_B + RING * sizeof(double);
-    static bool attr_set[2][2];
-    if (!attr_set[BWD][DOT]) {
+    static bool attr_set[IFL_MAX_DEVICES][2][2]; // function attributes are per device
+    if (!attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT]) {
         IFL_CUDA(cudaFuncSetAttribute(k_sweep3<BWD, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        attr_set[BWD][DOT] = true;
+        attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT] = true;
     }
     ProfScope ps_(c, BWD ? IFL_K_PRECON_BWD : IFL_K_PRECON_FWD);
     k_sweep3<BWD, DOT><<<P.nloc, 32, smem, c->stream>>>(P);

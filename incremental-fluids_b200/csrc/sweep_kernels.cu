@@ -943,13 +943,13 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     P.times = c->sweep_times;
     const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double);
     const bool masked = P.mask_tile >= 0;
-    static bool attr_set[5][2][2];
-    if (!attr_set[KIND][DOT][masked]) {
+    static bool attr_set[IFL_MAX_DEVICES][5][2][2]; // function attributes are per device
+    if (!attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked]) {
         IFL_CUDA(masked ? cudaFuncSetAttribute(k_sweep<KIND, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                227 * 1024 - 1024)
                         : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                227 * 1024 - 1024));
-        attr_set[KIND][DOT][masked] = true;
+        attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked] = true;
     }
     ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
     cudaLaunchConfig_t cfg;
