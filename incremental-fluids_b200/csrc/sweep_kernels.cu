@@ -204,7 +204,7 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
         t = t - o.c * up;                  // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
         znew = t * o.d;                    // v3:285
-        sts_f64_p<ALWAYS>(p + 4 * TILE_BYTES, znew, active);
+        sts_f64_p<ALWAYS>(p, znew, active); // in place: the rhs tile becomes the result tile
         cr.c1 = o.b;
     } else if (KIND == KIND_BWD) {
         double t = o.a - o.b * cr.zprev; // v3:297  t -= aPlusX[idx]*precon[idx]*dst[idx+1]
@@ -597,7 +597,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
     const int nst = P.nst;
     const int stage_doubles = P.nt * TILE_DOUBLES;
     const int ncols = P.nbx * 32;
-    int swept = (KIND == KIND_FWD) ? 4 : ((KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? 3 : 0);
+    int swept = (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? 3 : 0;
     const double *last_row = smem + swept * TILE_DOUBLES + G::lane_row(31) * TP; // tile row of the strip's last row
     const bool remote = sj + 1 == P.sj_base + P.nloc; // the downstream strip belongs to another rank
     uint4 *out = (remote ? P.handoff_down : P.handoff) + (size_t)sj * ncols;
@@ -897,7 +897,8 @@ void sweep_free(ifl_ctx *c) {
 struct TileSpec {
     const Arr *a;
     int load, row_shift, store;
-    const Arr *a2; // optional second store target (non-zero values only)
+    const Arr *a2;       // optional second store target (non-zero values only)
+    const Arr *store_to; // store target when it is not the array the tile was loaded from
 };
 
 template <int KIND, bool DOT>
@@ -905,7 +906,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     P.nt = nt;
     P.nst = nst;
     for (int k = 0; k < nt; k++) {
-        P.t[k].p = spec[k].a->p;
+        P.t[k].p = spec[k].store_to ? spec[k].store_to->p : spec[k].a->p;
         P.t[k].load = spec[k].load;
         P.t[k].row_shift = spec[k].row_shift;
         P.t[k].store = spec[k].store;
@@ -949,6 +950,8 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
                                                227 * 1024 - 1024)
                         : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                227 * 1024 - 1024));
+        IFL_CUDA(masked ? cudaFuncSetAttribute(k_sweep<KIND, DOT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+                        : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked] = true;
     }
     ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
@@ -994,6 +997,19 @@ int launch_mic0_factor(ifl_ctx *c) {
 // chapters 4+ multiply by `pe` (precon with +0.0 at non-fluid cells) and store only fluid cells
 static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
 
+// Ring depth of the two triangular solves: 5 stages, one CTA per SM.  Measured alternative
+// (IFL_SWEEP_STAGES=3: 101 KB, two strips per SM for grids with more strips than SMs): slower,
+// 1.72 vs 1.33 ms per forward sweep at 8192^2 -- a 3-stage ring leaves the TMA loads one
+// macro-step (1.6 us) to land and the co-resident CTA does not hide the resulting stalls.
+static int solve_stages(ifl_ctx *c) {
+    (void)c;
+    if (const char *e = getenv("IFL_SWEEP_STAGES")) {
+        const int v = atoi(e);
+        if (v >= 3 && v <= 5) return v;
+    }
+    return 5;
+}
+
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
     if (c->sweep_v3) return launch_precon_forward3(c, dst, a, gated);
     if (c->sweep_v2) return launch_precon_forward2(c, dst, a, gated);
@@ -1001,12 +1017,12 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
     P.mask_tile = c->version >= 4 ? 3 : -1;
-    const TileSpec spec[5] = {{&a, 1, 0, 0, nullptr},
-                              {&c->cx, 1, 0, 0, nullptr},
-                              {&c->cy, 1, 0, 0, nullptr},
-                              {&precon_operand(c), 1, 0, 0, nullptr},
-                              {&dst, 0, 0, 1, nullptr}};
-    return launch_sweep<KIND_FWD, false>(c, P, spec, 5, 5);
+    // the rhs tile is updated in place and drained into dst
+    const TileSpec spec[4] = {{&a, 1, 0, 1, nullptr, &dst},
+                              {&c->cx, 1, 0, 0, nullptr, nullptr},
+                              {&c->cy, 1, 0, 0, nullptr, nullptr},
+                              {&precon_operand(c), 1, 0, 0, nullptr, nullptr}};
+    return launch_sweep<KIND_FWD, false>(c, P, spec, 4, solve_stages(c));
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
@@ -1016,17 +1032,17 @@ int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, boo
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
     P.mask_tile = c->version >= 4 ? 3 : -1;
-    const TileSpec spec[5] = {{&dst, 1, 0, 1, nullptr},
-                              {&c->cx, 1, 0, 0, nullptr},
-                              {&c->cy, 1, 0, 0, nullptr},
-                              {&precon_operand(c), 1, 0, 0, nullptr},
-                              {&r_for_dot, 1, 0, 0, nullptr}};
+    const TileSpec spec[5] = {{&dst, 1, 0, 1, nullptr, nullptr},
+                              {&c->cx, 1, 0, 0, nullptr, nullptr},
+                              {&c->cy, 1, 0, 0, nullptr, nullptr},
+                              {&precon_operand(c), 1, 0, 0, nullptr, nullptr},
+                              {&r_for_dot, 1, 0, 0, nullptr, nullptr}};
     if (with_dot) {
         P.partials = partials_next(c);
         c->n_partials = (c->H + 31) / 32;
-        return launch_sweep<KIND_BWD, true>(c, P, spec, 5, 5);
+        return launch_sweep<KIND_BWD, true>(c, P, spec, 5, solve_stages(c));
     }
-    return launch_sweep<KIND_BWD, false>(c, P, spec, 4, 5);
+    return launch_sweep<KIND_BWD, false>(c, P, spec, 4, solve_stages(c));
 }
 
 // ------------------------------------------------------- Gauss-Seidel projection ----
