@@ -343,7 +343,7 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.yvalid = y < P.H ? 1 : 0;
         gs.W = P.W;
         gs.ncols = P.nbx * 32;
-        gs.cluster = P.cs > 1 ? 1 : 0;
+        gs.cluster = 0; // the hand-off counter is always bumped by this CTA's own poller warp
     }
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
@@ -354,10 +354,7 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     fetch<KIND, DOT>(ops, row0, row0 + (uint32_t)DIR, halo0, lane);
     if (KIND == KIND_GS && !(1 < P.W)) ops.b = 0.0;
     if (has_up) {
-        if (P.cs > 1)
-            wait_counter<true>(halo_cols_addr, HG, dead, P.scal);
-        else
-            wait_counter<false>(halo_cols_addr, HG, dead, P.scal);
+        wait_counter<false>(halo_cols_addr, HG, dead, P.scal);
         ops.halo = lds_f64(halo0);
     }
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
@@ -453,9 +450,12 @@ __device__ void loader_warp(const SweepParams &P, double *smem, uint64_t *full, 
 // hand-off row is never overwritten while lane 0 may still read it.
 template <int KIND>
 __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int lane, volatile int *dead,
-                            unsigned *counters) {
+                            unsigned *counters, const uint4 *ll_ring) {
     typedef Geo<KIND> G;
-    const int nst = P.nst, nbx = P.nbx;
+    const int nbx = P.nbx;
+    // ll_ring != null: the upstream strip runs in the same thread-block cluster and stores its
+    // messages {lo, tag, hi, tag} straight into this CTA's shared memory (tag = block + 1: a ring
+    // slot is reused every HR blocks); otherwise they arrive through L2 / NVLink, one slot per column.
     const uint4 *up_row = P.handoff + (size_t)(sj - 1) * nbx * 32;
     const bool remote = sj == P.sj_base; // the upstream strip belongs to another rank
     const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
@@ -464,12 +464,23 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
         const int st = m % HR;
         if (m >= HR) wait_counter(progress_addr, (unsigned)(32 * (m - HR + 1)), dead, P.scal);
         const uint4 *src = up_row + (size_t)m * 32 + lane;
+        const uint32_t src_s = ll_ring ? smem_u32(ll_ring + st * 32 + lane) : 0;
+        const unsigned tag = ll_ring ? (unsigned)(m + 1) : P.epoch;
         bool have = false;
         unsigned published = 0; // columns of this block already released
         while (published < 32) {
             if (!have) {
                 double v;
-                if (remote ? ll_load_sys(src, P.epoch, v) : ll_load(src, P.epoch, v)) {
+                bool ok;
+                if (ll_ring) {
+                    unsigned a, b, c2, d;
+                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "r"(src_s) : "memory");
+                    v = __hiloint2double((int)c2, (int)a);
+                    ok = b == tag && d == tag;
+                } else {
+                    ok = remote ? ll_load_sys(src, tag, v) : ll_load(src, tag, v);
+                }
+                if (ok) {
                     halo_s[st * 32 + G::tcol(lane)] = v;
                     have = true;
                     polls = 0;
@@ -584,9 +595,9 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
 // -------------------------------------------------------------- publisher warp ----
 // Forwards the strip's last row to the downstream strip, HG columns at a time, as soon as
 // the compute warp's progress counter says they are final.
-//   * downstream strip in the same thread-block cluster: the values are stored straight
-//     into that CTA's hand-off ring (distributed shared memory) and its hand-off counter is
-//     bumped with a release store -- ~a few hundred cycles end to end, nothing goes through L2;
+//   * downstream strip in the same thread-block cluster: 16-byte messages {lo, tag, hi, tag}
+//     stored straight into that CTA's message ring (distributed shared memory), validated by its
+//     poller warp in its own shared memory -- no fence, nothing goes through L2;
 //   * otherwise: NCCL-LL style 16-byte messages {lo, epoch, hi, epoch} through L2, picked up
 //     by the downstream CTA's poller warp.
 // It holds each stage until its 32 columns have been sent (second arrival on done[]).
@@ -602,10 +613,9 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
     const bool remote = sj + 1 == P.sj_base + P.nloc; // the downstream strip belongs to another rank
     uint4 *out = (remote ? P.handoff_down : P.handoff) + (size_t)sj * ncols;
     const uint32_t progress_addr = smem_u32(&counters[0]);
-    const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs;
-    // downstream CTA's hand-off ring, hand-off counter and progress counter (same layout as ours)
-    const uint32_t r_halo = dsmem ? mapa(smem_u32(halo_s), rank + 1) : 0;
-    const uint32_t r_halo_cols = dsmem ? mapa(smem_u32(&counters[1]), rank + 1) : 0;
+    // downstream strip in the same cluster (and on the same rank): its LL ring and progress counter
+    const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs && !remote;
+    const uint32_t r_ll = dsmem ? mapa(smem_u32(halo_s + HR * 32), rank + 1) : 0;
     const uint32_t r_progress = dsmem ? mapa(smem_u32(&counters[0]), rank + 1) : 0;
     int down_progress = 0; // last value read from the downstream strip's own progress counter
     int sent = 0;        // columns forwarded so far
@@ -631,10 +641,14 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
                             break;
                         }
                     }
-                    if (c < upto)
-                        st_remote_f64(r_halo + (uint32_t)((blk % HR) * 32 + G::tcol(c & 31)) * 8u, row[G::tcol(c & 31)]);
-                    __syncwarp();
-                    if (lane == 0) st_remote_u32_release(r_halo_cols, (unsigned)upto);
+                    // flag-in-data message {lo, tag, hi, tag}, tag = block + 1: no fence, no counter
+                    if (c < upto) {
+                        const double v = row[G::tcol(c & 31)];
+                        const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v), tag = (unsigned)(blk + 1);
+                        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r_ll + (uint32_t)((blk % HR) * 32 + (c & 31)) * 16u),
+                                     "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+                                     : "memory");
+                    }
                 } else {
                     if (c < upto) {
                         if (remote)
@@ -689,6 +703,9 @@ __global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepP
         s_counters[0] = 0;
         s_counters[1] = 0;
     }
+    uint4 *ll_ring = reinterpret_cast<uint4 *>(halo_s + HR * 32); // [HR][32] messages from the cluster neighbour
+    if (P.cs > 1)
+        for (int i = threadIdx.x; i < HR * 32; i += blockDim.x) ll_ring[i] = make_uint4(0u, 0u, 0u, 0u); // tag 0 = empty
     __syncthreads();
     int ticket;
     if (P.cs > 1) {
@@ -732,11 +749,12 @@ __global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepP
         storer_warp<KIND, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
     } else if (warp == 3) {
         if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank);
-    } else if (warp == 5 && sj > 0 && rank == 0) {
+    } else if (warp == 5 && sj > 0) {
         // (warp 4 stays idle: it would share the compute warp's scheduler, and a spinning
         // neighbour costs the recurrence ~12 cycles per step, profiles/microbench/step.cu)
-        // first strip of a cluster: its upstream strip lives in another cluster and talks through L2
-        poller_warp<KIND>(P, halo_s, sj, lane, &s_dead, s_counters);
+        // first strip of a cluster: its upstream strip lives in another cluster (or on another
+        // rank) and talks through L2; the others receive their messages in shared memory
+        poller_warp<KIND>(P, halo_s, sj, lane, &s_dead, s_counters, (rank == 0 || sj == P.sj_base) ? nullptr : ll_ring);
     }
 }
 
@@ -855,14 +873,16 @@ int sweep_init(ifl_ctx *c) {
     IFL_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned long long)));
     IFL_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned long long)));
     IFL_CUDA(cudaMalloc(&c->sweep_times_buf, (size_t)nby * 16 * sizeof(unsigned long long)));
-    // Hand-off through cluster DSMEM is implemented and bit-exact, but measured SLOWER than the
-    // L2 message path on B200 (4096^2 backward sweep: 825 us with clusters of 8 vs 672 us
-    // without; the cluster-scope release store costs the publisher ~1.4 us per group, see
-    // profiles/r01_c_dsmem_experiment.txt).  Default: no clusters; IFL_SWEEP_CLUSTER=2|4|8 enables.
-    c->sweep_cluster = 1;
+    // Strips are launched in thread-block clusters of 8: inside a cluster the hand-off messages
+    // go straight into the downstream CTA's shared memory (flag-in-data, no fence), only every
+    // 8th hand-off travels through L2.  Measured at 4096^2 (backward sweep): 645 us without
+    // clusters, 583 / 563 / 555 us with clusters of 2 / 4 / 8.  (A first DSMEM version that
+    // bumped a remote counter with a cluster-scope release store was SLOWER than L2, 825 us:
+    // profiles/r01_c_dsmem_experiment.txt.)  IFL_SWEEP_CLUSTER=1|2|4|8 overrides.
+    c->sweep_cluster = 8;
     if (const char *e = getenv("IFL_SWEEP_CLUSTER")) {
         const int v = atoi(e);
-        if ((v == 1 || v == 2 || v == 4 || v == 8) && c->world == 1) c->sweep_cluster = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
     }
     // IFL_SWEEP_V2=1 selects the two-columns-per-step kernels (sweep2_kernels.cu) for the
     // triangular solves: bit-exact, but measured slower at 4096^2 (855 vs 702 us per sweep),
@@ -876,7 +896,7 @@ int sweep_init(ifl_ctx *c) {
     // shared-memory pipe with the shuffles; kept for A/B measurements.
     c->sweep_v3 = 0;
     if (const char *e = getenv("IFL_SWEEP_V3"))
-        if (atoi(e) == 1 && c->version <= 3 && c->sweep_cluster == 1 && !c->sweep_v2) c->sweep_v3 = 1;
+        if (atoi(e) == 1 && c->version <= 3 && !c->sweep_v2) c->sweep_v3 = 1;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -942,7 +962,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     c->sweep_launches++;
     P.scal = c->scal;
     P.times = c->sweep_times;
-    const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double);
+    const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double) + (P.cs > 1 ? (size_t)HR * 32 * sizeof(uint4) : 0);
     const bool masked = P.mask_tile >= 0;
     static bool attr_set[IFL_MAX_DEVICES][5][2][2]; // function attributes are per device
     if (!attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked]) {
