@@ -121,6 +121,7 @@ struct ifl_ctx {
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     int sweep_v2;                      // triangular solves use sweep2_kernels.cu
+    int fuse_axpy;                     // PCG: k_axpy2_norm rides inside the forward sweep (chapters 1-5)
     int sweep_v3;                      // triangular solves use sweep3_kernels.cu (one-warp CTAs, chapters 1-3)
     // row-slab multi-GPU: world == 1 unless the context came from ifl_create_dist
     int rank, world;
@@ -288,6 +289,7 @@ void sweep_free(ifl_ctx *c);
 int launch_mic0_factor(ifl_ctx *c);
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
+int launch_precon_forward_axpy(ifl_ctx *c); // fused p += alpha s; r -= alpha q; |r|inf; z = L^-1 r
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
 // sweep2_kernels.cu
 int launch_precon_forward2(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);

@@ -343,6 +343,20 @@ static int scalar_stage(ifl_ctx *c) {
 static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
+    if (c->fuse_axpy) {
+        // p += alpha s, r -= alpha q and |r|inf ride inside the forward sweep; the convergence
+        // test follows it (a converged solve has then computed one forward sweep it does not need)
+        IFL_TRY(launch_precon_forward_axpy(c));
+        IFL_TRY(scalar_stage<SC_CHECK>(c));
+        IFL_TRY(launch_precon_backward(c, c->z, c->r, true, true)); // partial z.r
+        IFL_TRY(scalar_stage<SC_BETA>(c));
+        {
+            ProfScope ps_(c, IFL_K_XPAY);
+            k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
+            IFL_LAUNCHED(c);
+        }
+        return dist_barrier(c, true);
+    }
     {
         ProfScope ps_(c, IFL_K_AXPY2_NORM);
         k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, partials_next(c),

@@ -51,7 +51,12 @@
 
 namespace ifl {
 
-enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3, KIND_FACTOR_M = 4 }; // _M: with solid cells (v5:715-744)
+enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3, KIND_FACTOR_M = 4, KIND_FWD_AXPY = 5 }; // _M: with solid cells (v5:715-744)
+// KIND_FWD_AXPY: forward substitution fused with the two scaledAdds and the infinityNorm that precede it
+// in the PCG loop (v3:363-366): r += q*(-alpha) on the fly (tile 4 holds q = A*s and receives the new r),
+// |r|inf folded by the storer warp while it drains that tile, p += s*alpha streamed by a warp of its own.
+// The sweep is bound by its dependency chain and leaves ~85 % of the HBM bandwidth idle, so the 48 B/cell
+// of k_axpy2_norm ride along for free instead of costing a kernel of their own.
 
 // A tile is one TMA box: 33 rows x 32 doubles, dense (256-byte rows).  Forward kinds
 // fetch memory rows y0-1 .. y0+31 (tile row 0 = the upstream strip's last row, lane t
@@ -93,6 +98,8 @@ struct SweepParams {
     SolveScalars *scal;
     int gated;        // skip when scal->done
     double *partials; // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
+    double *p_upd;       // KIND_FWD_AXPY: p (updated by the p-updater warp)
+    const double *s_upd; // KIND_FWD_AXPY: s
     double scale;     // KIND_GS: timestep/(density*hx*hx)  v2:234
     int mask_tile;    // >= 0: results are stored only where this tile is non-zero (fluid cells), else -1
     int cs;           // thread-block cluster size (1 = no cluster): strips of one cluster hand off through DSMEM
@@ -134,11 +141,12 @@ __device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint
         o.b = lds_f64(p_right);            // p (old)  right cell
         o.c = lds_f64(p + 1 * TILE_BYTES); // p (old)  lower cell (tile 1 = p fetched one row down)
         o.d = lds_f64(p + 2 * TILE_BYTES); // r        own cell
-    } else if (KIND == KIND_FWD) {
+    } else if (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) {
         o.a = lds_f64(p);                       // a (rhs)  own cell
         o.b = lds_f64(p + 1 * TILE_BYTES);      // cx       own cell (carried to the next step)
         o.c = lds_f64(p + 2 * TILE_BYTES + UP); // cy       upper cell
         o.d = lds_f64(p + 3 * TILE_BYTES);      // precon   own cell
+        if (KIND == KIND_FWD_AXPY) o.e = lds_f64(p + 4 * TILE_BYTES); // q = A*s own cell
     } else if (KIND == KIND_BWD) {
         o.a = lds_f64(p);                            // z (forward result) own cell, updated in place
         o.b = lds_f64(p + 1 * TILE_BYTES);           // cx own
@@ -164,6 +172,7 @@ struct GsConst {
     int W;
     int ncols;             // padded sweep width (32 * nbx)
     int cluster;           // hand-off counter is bumped remotely (DSMEM): needs acquire loads
+    double nalpha;         // KIND_FWD_AXPY: -alpha of this PCG iteration (v3:364)
 };
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
@@ -200,8 +209,13 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         znew = (o.d - off) / diag;       // v2:267
         if (gs.yvalid && c < gs.W && (ALWAYS || active)) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
         sts_f64_p<ALWAYS>(p, znew, active); // v2:271
-    } else if (KIND == KIND_FWD) {
-        double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
+    } else if (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) {
+        double rhs = o.a;
+        if (KIND == KIND_FWD_AXPY) {
+            rhs = o.a + o.e * gs.nalpha;                         // v3:364  r[i] = r[i] + z[i]*(-alpha)   (z holds A*s)
+            sts_f64_p<ALWAYS>(p + 4 * TILE_BYTES, rhs, active); // the q tile becomes the new r
+        }
+        double t = rhs - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
         t = t - o.c * up;                  // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
         znew = t * o.d;                    // v3:285
         sts_f64_p<ALWAYS>(p, znew, active); // in place: the rhs tile becomes the result tile
@@ -344,6 +358,7 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.W = P.W;
         gs.ncols = P.nbx * 32;
         gs.cluster = 0; // the hand-off counter is always bumped by this CTA's own poller warp
+        gs.nalpha = (KIND == KIND_FWD_AXPY) ? -P.scal->alpha : 0.0;
     }
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
@@ -524,6 +539,7 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
     const int half = lane >> 4, l16 = lane & 15;
     const int toff = (G::BWD ? half : 1 + half) * TP + l16 * 2; // this lane's first element inside a tile
     double acc = 0.0;
+    double nrm = 0.0; // KIND_FWD_AXPY: max |r| over this lane's cells (v3:366)
     for (int m = 0; m < P.nbx; m++) {
         const int st = m % nst;
         const double *stage = smem + st * stage_doubles;
@@ -546,8 +562,15 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
                     acc += v[i].y * rv.y;
                 }
             }
+            if (KIND == KIND_FWD_AXPY && k == 4) { // the new r: fold infinityNorm (pad cells hold +0.0)
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    nrm = std_max(nrm, fabs(v[i].x));
+                    nrm = std_max(nrm, fabs(v[i].y));
+                }
+            }
             double *g = P.t[k].p + x + (size_t)(y0 + half) * P.pitch;
-            if (!MASKED || KIND == KIND_FACTOR_M) {
+            if (!MASKED || KIND == KIND_FACTOR_M || (KIND == KIND_FWD_AXPY && k == 4)) { // (r is a plain vector: never masked)
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     double *dst = g + (size_t)(i * 2) * P.pitch;
@@ -589,6 +612,40 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
     if (DOT) {
         const double sum = warp_sum(acc);
         if (lane == 0) P.partials[sj] = sum;
+    }
+    if (KIND == KIND_FWD_AXPY) {
+        const double mx = warp_max(nrm);
+        if (lane == 0) P.partials[sj] = mx;
+    }
+}
+
+// ------------------------------------------------------------------ p-updater ----
+// KIND_FWD_AXPY: p += s*alpha (v3:363) over the strip's 32 rows, a plain HBM stream that has
+// nothing to do with the wavefront; it lives in a warp of its own so that it never delays the
+// ring (the sweep leaves most of the HBM bandwidth idle anyway).
+__device__ void p_update_warp(const SweepParams &P, int sj, int lane) {
+    const double alpha = P.scal->alpha;
+    const int y0 = sj * 32, y1 = imin(y0 + 32, P.H);
+    const int npairs = P.pitch / 2; // pad columns hold zeros on both sides: p stays zero there
+    for (int y = y0; y < y1; y++) {
+        double2 *pr = reinterpret_cast<double2 *>(P.p_upd + (size_t)y * P.pitch);
+        const double2 *sr = reinterpret_cast<const double2 *>(P.s_upd + (size_t)y * P.pitch);
+        for (int i0 = 0; i0 < npairs; i0 += 128) {
+            double2 pv[4], sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * 32 + lane;
+                if (i < npairs) {
+                    pv[u] = pr[i];
+                    sv[u] = sr[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * 32 + lane;
+                if (i < npairs) pr[i] = make_double2(pv[u].x + sv[u].x * alpha, pv[u].y + sv[u].y * alpha);
+            }
+        }
     }
 }
 
@@ -682,7 +739,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
 
 // ---------------------------------------------------------------------- kernel ----
 template <int KIND, bool DOT, bool MASKED>
-__global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(224, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
     __shared__ int s_ticket;
@@ -749,6 +806,8 @@ __global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepP
         storer_warp<KIND, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
     } else if (warp == 3) {
         if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank);
+    } else if (warp == 6) {
+        if (KIND == KIND_FWD_AXPY) p_update_warp(P, sj, lane);
     } else if (warp == 5 && sj > 0) {
         // (warp 4 stays idle: it would share the compute warp's scheduler, and a spinning
         // neighbour costs the recurrence ~12 cycles per step, profiles/microbench/step.cu)
@@ -897,6 +956,14 @@ int sweep_init(ifl_ctx *c) {
     c->sweep_v3 = 0;
     if (const char *e = getenv("IFL_SWEEP_V3"))
         if (atoi(e) == 1 && c->version <= 3 && !c->sweep_v2) c->sweep_v3 = 1;
+    // IFL_FUSE_AXPY=1 (chapters 3-5: plain, unmasked vector helpers) fuses v3:363-366 into the
+    // forward sweep (KIND_FWD_AXPY).  Bit-exact, but OFF by default: at 4096^2 the fused sweep
+    // takes 0.746 ms against 0.567 + 0.125 ms for the sweep and k_axpy2_norm on their own -- one
+    // more operand load, store and two FP64 ops per step in the in-order compute warp, a fifth
+    // tile in the TMA ring and a streaming warp next to it cost more than the kernel they save.
+    c->fuse_axpy = 0;
+    if (const char *e = getenv("IFL_FUSE_AXPY"))
+        if (atoi(e) == 1 && c->version >= 3 && c->version <= 5 && !c->sweep_v2 && !c->sweep_v3) c->fuse_axpy = 1;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -964,7 +1031,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     P.times = c->sweep_times;
     const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double) + (P.cs > 1 ? (size_t)HR * 32 * sizeof(uint4) : 0);
     const bool masked = P.mask_tile >= 0;
-    static bool attr_set[IFL_MAX_DEVICES][5][2][2]; // function attributes are per device
+    static bool attr_set[IFL_MAX_DEVICES][6][2][2]; // function attributes are per device
     if (!attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked]) {
         IFL_CUDA(masked ? cudaFuncSetAttribute(k_sweep<KIND, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                227 * 1024 - 1024)
@@ -974,11 +1041,11 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
                         : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked] = true;
     }
-    ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
+    ProfScope ps_(c, (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(KIND == KIND_FWD_AXPY ? 224 : 192); // + the p-updater warp
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -1043,6 +1110,25 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
                               {&c->cy, 1, 0, 0, nullptr, nullptr},
                               {&precon_operand(c), 1, 0, 0, nullptr, nullptr}};
     return launch_sweep<KIND_FWD, false>(c, P, spec, 4, solve_stages(c));
+}
+
+// One launch for v3:363-366 + the forward half of v3:372: p += alpha*s, r -= alpha*q, |r|inf
+// (-> partials) and z = forward substitution of the NEW r.  alpha is read from scal->alpha.
+int launch_precon_forward_axpy(ifl_ctx *c) {
+    SweepParams P;
+    memset(&P, 0, sizeof P);
+    P.gated = 1;
+    P.mask_tile = c->version >= 4 ? 3 : -1;
+    const TileSpec spec[5] = {{&c->r, 1, 0, 1, nullptr, &c->z},
+                              {&c->cx, 1, 0, 0, nullptr, nullptr},
+                              {&c->cy, 1, 0, 0, nullptr, nullptr},
+                              {&precon_operand(c), 1, 0, 0, nullptr, nullptr},
+                              {&c->q, 1, 0, 1, nullptr, &c->r}};
+    P.p_upd = c->p.p;
+    P.s_upd = c->s.p;
+    P.partials = partials_next(c);
+    c->n_partials = (c->H + 31) / 32;
+    return launch_sweep<KIND_FWD_AXPY, false>(c, P, spec, 5, solve_stages(c));
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
