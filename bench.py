@@ -103,11 +103,18 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ CPU reference ----
-def cpu_reference_sample(size, cap_iters, full_iters):
+CPU_SAMPLE_SIDE = 4096  # the CPU arm never times a grid larger than this (a 4096^2 sample already takes ~20 s)
+
+
+def cpu_reference_sample(full_size, cap_iters, full_iters):
     """Times the reference's CPU path on a bounded sample of the workload: assembly +
-    project(limit=cap_iters) + applyPressure + 3x advect at full size, one core.
+    project(limit=cap_iters) + applyPressure + 3x advect, one core, on a grid of at most
+    CPU_SAMPLE_SIDE^2 cells (every stage is a streaming pass far above the cache sizes, so the
+    time per cell does not depend on the grid; larger workloads are scaled by their cell count).
     Returns (seconds per FULL step extrapolated to `full_iters` PCG iterations, detail)."""
     from oracle import refapi
+    size = min(full_size, CPU_SAMPLE_SIDE)
+    cell_scale = (full_size / float(size)) ** 2
     use_ref = refapi.available(3)
     if use_ref:
         s = refapi.Ref(3, size, size, [DENSITY])
@@ -142,11 +149,13 @@ def cpu_reference_sample(size, cap_iters, full_iters):
     timed("advect", ops["advect"])
     per_iter = max(t["projectN"] - t["project0"], 1e-9) / max(cap_iters, 1)
     fixed = t["rhs"] + t["matrix"] + t["precon"] + t["project0"] + t["pressure"] + t["advect"]
-    step = fixed + per_iter * full_iters
+    step = (fixed + per_iter * full_iters) * cell_scale
     detail = ("%s CPU code, 1 thread, %dx%d: assembly+prologue+applyPressure+3 advects timed in full (%.2f s), "
               "%d PCG iterations timed (%.3f s/iter), extrapolated to the %d iterations of the device step"
               % ("unmodified reference (oracle/_ref)" if use_ref else "C port of the reference (oracle/ifl_oracle.c)",
                  size, size, fixed, cap_iters, per_iter, full_iters))
+    if cell_scale != 1.0:
+        detail += "; scaled by %.2f (cells of the %dx%d workload / cells of the sample)" % (cell_scale, full_size, full_size)
     if use_ref:
         s.close()
     return step, kind, detail
@@ -157,7 +166,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     size = grid_side(args, args.gpus)
-    cap = args.cpu_iters
+    cap = min(args.cpu_iters, 3)  # ~18 s per sampled step: W + K steps end within a few minutes
     times = []
     kind = detail = None
     for i in range(args.warmup + args.steps):
