@@ -45,6 +45,12 @@
 #include "ifl_internal.cuh"
 #include "sweep_common.cuh"
 
+// 1: the compute warp also records a timestamp every nbx/8 macro-steps (ifl_debug_sweep_times slots
+// 2..10).  Off by default: even this one branch per macro-step shifts the hot loop's code generation.
+#ifndef IFL_SWEEP_DIAG
+#define IFL_SWEEP_DIAG 0
+#endif
+
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -375,13 +381,17 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
     int sp = 0, sc = 0, sn = (nst > 1) ? 1 : 0; // stages of blocks m-1, m, m+1
     unsigned par_next = 0;                        // parity of full[sn] for block m+1
     const int probe = (nbx / 2) * 32; // diagnostics: hand-off timestamps for the group ending at this column
+#if IFL_SWEEP_DIAG
     const int ck = (nbx + 7) / 8; // diagnostics: a timestamp every nbx/8 macro-steps
+#endif
     for (int m = 0; m <= nbx; m++) {
+#if IFL_SWEEP_DIAG
         if (P.times && lane == 0 && (m % ck) == 0 && m / ck < 12) {
             unsigned long long tt;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt));
             P.times[16 * sj + 2 + m / ck] = tt;
         }
+#endif
         const bool has_next = m + 1 < nbx;
         const uint32_t s_prev = row0 + sp * stage_bytes;
         const uint32_t s_cur = row0 + sc * stage_bytes;
