@@ -728,6 +728,9 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
                 if (sent == blk_end) { // all 32 columns of this block are out: the stage may drain
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[st]);
+                    // refresh the downstream strip's progress off the critical path: the value is
+                    // first needed when the next block's ring slot is checked, a block from now
+                    if (dsmem && blk + 1 >= HR && blk + 1 < P.nbx) down_progress = (int)ld_remote_u32(r_progress); // (not after the last block: the downstream CTA may be gone)
                     blk++;
                     if (++st == nst) st = 0;
                     row = last_row + st * stage_doubles;
@@ -736,7 +739,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
             if (P.times && lane == 0 && prog == (P.nbx / 2) * 32)
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(P.times[16 * sj + 12]));
             n = 0;
-        } else if (++n > WATCHDOG_POLLS || *dead) {
+        } else if (++n > WATCHDOG_POLLS || ((n & 63u) == 0 && *dead)) {
             *dead = 1;
             P.scal->watchdog = 1;
             // release every stage so that the other warps can finish
