@@ -15,29 +15,32 @@
 // `_aPlusX[i]*_precon[i]*dst[i]` left to right (v3:281), so this is the same product.
 //
 // Execution model (B200: 148 SMs, 227 KB smem/SM, 1 CTA per SM):
-//   * The padded grid is cut into strips of 32 rows.  One CTA owns one strip and
-//     walks it in 32-column blocks.  Strips are handed out by an atomic ticket, so a
-//     running CTA only ever waits on strips that are already running or finished
-//     (no co-residency assumption, no deadlock).
-//   * Inside the CTA five warps are specialised (compute, TMA loader, storer, publisher,
-//     hand-off poller; the last two exist so that the compute warp issues nothing but
-//     the recurrence itself):
-//       warp 0 (compute): lane t owns row t of the strip and is skewed t columns
-//         behind lane t-1, i.e. the warp is one anti-diagonal.  The left neighbour is
-//         the lane's own previous value (register), the upper neighbour arrives by
-//         __shfl_up.  Operands are read from shared-memory tiles at skewed addresses
-//         (dense 32-double rows: the skew itself staggers the banks), one step ahead of their use, so the
-//         per-step cost is the 4-deep dependent FP64 chain and nothing else.
-//       warp 1 (loader): streams the strip's operand tiles HBM -> smem with 2-D
-//         tensor-map TMA (cp.async.bulk.tensor, one 33x32 box per operand per block)
-//         into an N-stage ring, N-2 blocks ahead of the compute warp, and polls the
-//         upstream strip's last row out of the hand-off buffer.
-//       warp 2 (storer): drains finished result tiles smem -> HBM with 16-byte stores.
+//   * The padded grid is cut into strips of 32 rows.  One CTA owns one strip and walks it in
+//     32-column blocks.  Strips are handed out by an atomic ticket (one per thread-block
+//     cluster of 8 CTAs = 8 consecutive strips), so a running CTA only ever waits on strips
+//     that are already running or finished (no co-residency assumption, no deadlock).
+//   * Inside the CTA the warps are specialised so that the compute warp issues nothing but
+//     the recurrence itself (warp 4 stays empty: it would share the compute warp's scheduler):
+//       warp 0 (compute): lane t owns row t of the strip and is skewed t columns behind lane
+//         t-1, i.e. the warp is one anti-diagonal.  The left neighbour is the lane's own
+//         previous value (register), the upper neighbour arrives by __shfl_up.  Operands are
+//         read from shared-memory tiles at skewed addresses (dense 32-double rows: the skew
+//         itself staggers the banks), one step ahead of their use.  The forward and backward
+//         solves update their swept tile in place.
+//       warp 1 (loader): streams the strip's operand tiles HBM -> smem with 2-D tensor-map
+//         TMA (cp.async.bulk.tensor, one 33x32 box per operand per block) into an N-stage ring.
+//       warp 2 (storer): drains finished result tiles smem -> HBM with 16-byte stores and folds
+//         dotProduct(z, r) for the backward solve.
+//       warp 3 (publisher) / warp 5 (poller): the strip-to-strip hand-off, below.
+//       (warp 6, KIND_FWD_AXPY only: streams p += alpha*s.)
 //     Stages are recycled through mbarriers (full / done / empty).
-//   * Strip-to-strip hand-off of the swept variable uses NCCL-LL style 16-byte
-//     messages {lo, epoch, hi, epoch}: the last lane publishes every value the moment
-//     it is computed, the consumer validates both epochs, and no fence sits on the
-//     critical path.  Epochs are unique per launch.
+//   * Strip-to-strip hand-off of the swept variable: NCCL-LL style 16-byte messages
+//     {lo, tag, hi, tag}, 8 columns at a time, validated by the consumer's poller warp and
+//     released to its compute warp through a shared counter; no fence sits on the critical
+//     path.  Inside a cluster the publisher stores the messages straight into the downstream
+//     CTA's shared memory (st.shared::cluster, tag = block number); between clusters -- and
+//     between the slabs of two GPUs (dist.cu) -- they go through L2 / NVLink into a hand-off
+//     array with a per-launch epoch as tag.
 //   * Cells of the padded border (x >= w or y >= h) are swept too; they only ever see
 //     +0.0 operands, which makes `t - c*z` an exact no-op for the real boundary cells
 //     (the reference skips those terms, v3:280-283), so the inner loop has no
