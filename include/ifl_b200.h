@@ -149,8 +149,9 @@ int ifl_profile_read(ifl_ctx *ctx, double *ms, long long *launches);
 
 /* Diagnostics for the wavefront kernels: arm != 0 makes every following sweep record the
  * %globaltimer (ns) at which each 32-row strip started and finished; arm == 0 disarms,
- * copies the last sweep's [strips][16] table (start, end, then a timestamp every 1/8 of
- * the strip) into out_ns and returns the strip count. */
+ * copies the last sweep's [strips][16] table (slot 0 start, 1 end, 15 SM cycles of the compute
+ * warp; slots 2..10 hold a timestamp every 1/8 of the strip only in builds with
+ * -DIFL_SWEEP_DIAG=1, the probe costs the hot loop 3 %) into out_ns and returns the strip count. */
 int ifl_debug_sweep_times(ifl_ctx *ctx, int arm, unsigned long long *out_ns, int capacity);
 
 /* ---- data movement (backs FluidQuantity::at()/src(), toImage, test harness) ---- */
