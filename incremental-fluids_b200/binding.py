@@ -57,7 +57,8 @@ EXPORTS = [
 
 
 def library_path():
-    return os.path.join(HERE, _LIB_NAME)
+    # IFL_B200_LIB: an alternative build of the same library (profiles/tri_experiments.sh)
+    return os.environ.get("IFL_B200_LIB") or os.path.join(HERE, _LIB_NAME)
 
 
 def build_library(verbose=False):
@@ -372,7 +373,7 @@ class FluidSolver:
         n = self.L.ifl_debug_sweep_times(self.ctx, 0, buf.ctypes.data, buf.size)
         if n < 0:
             self._chk(n)
-        return buf.reshape(-1, 16)
+        return buf.reshape(-1, 16)[:n]
 
     # ---- private hot-path methods of the reference class
     def buildRhs(self):

@@ -1,6 +1,6 @@
 // dist.cu -- row-slab multi-GPU plumbing: one process per GPU, ONE address space.
 //
-// The grid is split into slabs of whole 32-row strips.  Instead of exchanging
+// The grid is split into slabs of whole 64-row strips.  Instead of exchanging
 // halo rows, every array lives in one virtual address range that all ranks map identically:
 // the pages holding a slab are physical HBM of the slab's owner (cuMemCreate), exported as
 // POSIX file descriptors, passed between the processes over a UNIX socket (SCM_RIGHTS) and
@@ -33,14 +33,15 @@
 namespace ifl {
 
 // ------------------------------------------------------------------ slab plan ----
-// Strips of 32 rows are dealt to the ranks in contiguous runs: rank g owns strips
+// Strips of 64 rows (the unit of the triangular-solve engine, tri_kernels.cu; two strips of the
+// one-row engine) are dealt to the ranks in contiguous runs: rank g owns strips
 // [floor(S*g/G), floor(S*(g+1)/G)).  Rows of the wider arrays (v and phi have h+1 rows)
 // follow the cell rows; everything past the last boundary belongs to the last rank.
 static int slab_first_strip(int h, int world, int g) {
-    const long long strips = (h + 31) / 32;
+    const long long strips = (h + 63) / 64;
     return (int)(strips * g / world);
 }
-static int slab_row0(int h, int world, int g) { return g >= world ? (1 << 30) : 32 * slab_first_strip(h, world, g); }
+static int slab_row0(int h, int world, int g) { return g >= world ? (1 << 30) : 64 * slab_first_strip(h, world, g); }
 static int rank_of_row(int h, int world, long long row) {
     int g = 0;
     while (g + 1 < world && row >= slab_row0(h, world, g + 1)) g++;
@@ -463,8 +464,8 @@ int dist_init(ifl_ctx *c, int rank, int world, const char *rendezvous) {
         set_error("ifl_create_dist: rank %d of %d (at most %d ranks) needs a rendezvous path", rank, world, MAX_WORLD);
         return IFL_E_ARG;
     }
-    if ((c->H + 31) / 32 < world) {
-        set_error("ifl_create_dist: %d rows give fewer than %d strips of 32 rows", c->H, world);
+    if ((c->H + 63) / 64 < world) {
+        set_error("ifl_create_dist: %d rows give fewer than %d strips of 64 rows", c->H, world);
         return IFL_E_ARG;
     }
     Drv *v = drv();
@@ -529,7 +530,7 @@ using namespace ifl;
 extern "C" {
 
 int ifl_dist_plan(int h, int world, int rank, int *row0, int *row1) {
-    if (h < 2 || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || (h + 31) / 32 < world) {
+    if (h < 2 || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || (h + 63) / 64 < world) {
         set_error("ifl_dist_plan: bad argument (h=%d world=%d rank=%d)", h, world, rank);
         return IFL_E_ARG;
     }

@@ -140,6 +140,22 @@ static Arr *buf_arr(ifl_ctx *c, int buf) {
 
 static bool pcg_chapter(const ifl_ctx *c) { return c->version >= 3; }
 
+// The sticky watchdog word (SolveScalars::watchdog) is raised by any in-kernel dependency wait that
+// timed out: a sweep hand-off, a TMA ring barrier, a rank barrier between stages.  The solves look
+// at it in their own read-backs; everything else (the factorisation, the stage barriers of
+// update()) is caught here, at the end of every entry point that launches such kernels.
+int check_watchdog(ifl_ctx *c, const char *where) {
+    int *h = reinterpret_cast<int *>(c->result_h + 7);
+    IFL_CUDA(cudaMemcpyAsync(h, &c->scal->watchdog, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    if (*h) {
+        cudaMemsetAsync(&c->scal->watchdog, 0, sizeof(int), c->stream);
+        set_error("%s: a dependency wait (wavefront hand-off or rank barrier) timed out", where);
+        return IFL_E_WATCHDOG;
+    }
+    return IFL_OK;
+}
+
 } // namespace ifl
 
 using namespace ifl;
@@ -355,7 +371,7 @@ int ifl_debug_sweep_times(ifl_ctx *c, int arm, unsigned long long *out_ns, int c
     IFL_CUDA(cudaStreamSynchronize(c->stream));
     IFL_CUDA(cudaMemcpy(out_ns, c->sweep_times_buf, (size_t)16 * c->n_strips * sizeof(unsigned long long),
                         cudaMemcpyDeviceToHost));
-    return c->n_strips;
+    return c->tri_engine ? (c->H + 63) / 64 : c->n_strips; // strips of the engine that ran the triangular solves
 }
 
 long long ifl_launch_count(const ifl_ctx *c) { return c ? c->launches : 0; }
@@ -751,7 +767,8 @@ int ifl_build_preconditioner(ifl_ctx *c) {
     CHECK_CTX(c);
     TRY(need_pcg(c, "ifl_build_preconditioner"));
     TRY(dist_barrier(c));
-    return launch_mic0_factor(c);
+    TRY(launch_mic0_factor(c));
+    return check_watchdog(c, "ifl_build_preconditioner");
 }
 
 int ifl_apply_preconditioner(ifl_ctx *c, int dst, int a) {
@@ -765,13 +782,7 @@ int ifl_apply_preconditioner(ifl_ctx *c, int dst, int a) {
     TRY(dist_barrier(c));
     TRY(launch_precon_forward(c, *d, *s, false));
     TRY(launch_precon_backward(c, *d, *s, false, false));
-    IFL_CUDA(cudaMemcpyAsync(c->scal_h, c->scal, sizeof(SolveScalars), cudaMemcpyDeviceToHost, c->stream));
-    IFL_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->scal_h[0].watchdog) {
-        set_error("ifl_apply_preconditioner: wavefront dependency watchdog fired");
-        return IFL_E_WATCHDOG;
-    }
-    return IFL_OK;
+    return check_watchdog(c, "ifl_apply_preconditioner");
 }
 
 int ifl_matrix_vector_product(ifl_ctx *c, int dst, int b) {
@@ -934,8 +945,7 @@ static int update_heat(ifl_ctx *c, double timestep, ifl_solve_info *infos) {
 }
 #undef B
 
-int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
-    CHECK_CTX(c);
+static int update_impl(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
     ifl_solve_info local;
     ifl_solve_info *info = infos ? infos : &local;
     if (c->version >= 8) {
@@ -968,6 +978,14 @@ int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *info
     TRY(ifl_flip(c, IFL_FIELD_U));
     TRY(ifl_flip(c, IFL_FIELD_V));
     return IFL_OK;
+}
+
+int ifl_update(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
+    CHECK_CTX(c);
+    TRY(update_impl(c, timestep, density, infos));
+    // one stream synchronisation per step: a timed-out stage barrier or factorisation sweep must not
+    // go unnoticed (the solves check the same sticky word in their own read-backs)
+    return check_watchdog(c, "ifl_update");
 }
 
 // slab != 0: the host buffers hold only this rank's rows (row ry0 of each array first)

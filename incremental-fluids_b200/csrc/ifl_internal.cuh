@@ -69,7 +69,10 @@ struct SolveScalars {
     double max_error; // |r|inf       v3:366
     int iter;         // zero-based iteration counter (what v3:368 prints)
     int done;         // 0 running, 1 converged, 2 initial-small
-    int watchdog;     // set by a dependency wait that ran out
+    // ---- everything above is reset at the start of a solve; the watchdog word is STICKY: set by
+    // any dependency wait that timed out (sweep hand-off, rank barrier), cleared only by the host
+    // after it has reported IFL_E_WATCHDOG (check_watchdog, ifl_api.cu)
+    int watchdog;
     int pad;
 };
 
@@ -120,9 +123,8 @@ struct ifl_ctx {
     unsigned long long sweep_launches; // sweeps launched so far
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
-    int sweep_v2;                      // triangular solves use sweep2_kernels.cu
-    int fuse_axpy;                     // PCG: k_axpy2_norm rides inside the forward sweep (chapters 1-5)
-    int sweep_v3;                      // triangular solves use sweep3_kernels.cu (one-warp CTAs, chapters 1-3)
+    int tri_engine;                    // 1: triangular solves run on tri_kernels.cu (64-row strips)
+    int sweep_head_delay;              // SM cycles the head strip idles per macro-step (pace-setter, sweep_init)
     // row-slab multi-GPU: world == 1 unless the context came from ifl_create_dist
     int rank, world;
     int ry0, ry1;                // cell rows [ry0, ry1) owned by this rank (multiples of 32, ry1 clipped to H)
@@ -239,14 +241,19 @@ __device__ __forceinline__ void dist_barrier_block(const DistDev &d) {
     if ((int)threadIdx.x < d.world) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.flags_peer[threadIdx.x] + d.rank), "l"(e) : "memory");
-        unsigned long long v = 0;
+        unsigned long long v = 0, t_first = 0;
         unsigned n = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.flags_local + threadIdx.x) : "memory");
             if (v >= e) break;
-            if (++n > (1u << 24)) { // a peer died: raise the watchdog instead of hanging the GPU
-                *d.watchdog = 1;
-                break;
+            if ((++n & 1023u) == 0) { // a peer died: raise the watchdog instead of hanging the GPU (2 s, by the clock)
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t_first == 0) t_first = now;
+                if (now - t_first > 2000000000ull) {
+                    *d.watchdog = 1;
+                    break;
+                }
             }
         }
     }
@@ -276,6 +283,8 @@ void dist_free_mem(ifl_ctx *c, void *p);
 int dist_barrier(ifl_ctx *c, bool gated = false); // stream-ordered barrier across the ranks (no-op when world == 1); gated: skipped once scal->done
 int dist_host_barrier(ifl_ctx *c); // host-side barrier through the rendezvous sockets
 int dist_host_sum(ifl_ctx *c, long long *v); // host-side all-reduce (sum) of one integer
+// ifl_api.cu
+int check_watchdog(ifl_ctx *c, const char *where); // synchronises the stream; IFL_E_WATCHDOG (and clears the word) if a wait timed out
 // pcg_kernels.cu
 int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot);
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b);
@@ -289,14 +298,11 @@ void sweep_free(ifl_ctx *c);
 int launch_mic0_factor(ifl_ctx *c);
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
-int launch_precon_forward_axpy(ifl_ctx *c); // fused p += alpha s; r -= alpha q; |r|inf; z = L^-1 r
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
-// sweep2_kernels.cu
-int launch_precon_forward2(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
-int launch_precon_backward2(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
-// sweep3_kernels.cu
-int launch_precon_forward3(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
-int launch_precon_backward3(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
+// tri_kernels.cu: the two-rows-per-lane engine of the triangular solves (default; IFL_TRI=0 selects the
+// one-row engine of sweep_kernels.cu for A/B measurements)
+int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
+int launch_tri_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 // solid_kernels.cu (chapters 4+)
 int launch_fill_solid_fields(ifl_ctx *c, int field);
 int launch_set_boundary_condition(ifl_ctx *c);

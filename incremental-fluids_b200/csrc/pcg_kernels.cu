@@ -19,6 +19,7 @@
 // kernels without a read-after-write hazard.  ifl_download(IFL_BUF_Z) is unaffected.
 #include "ifl_internal.cuh"
 
+#include <stddef.h>
 #include <string.h>
 
 namespace ifl {
@@ -343,20 +344,6 @@ static int scalar_stage(ifl_ctx *c) {
 static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
-    if (c->fuse_axpy) {
-        // p += alpha s, r -= alpha q and |r|inf ride inside the forward sweep; the convergence
-        // test follows it (a converged solve has then computed one forward sweep it does not need)
-        IFL_TRY(launch_precon_forward_axpy(c));
-        IFL_TRY(scalar_stage<SC_CHECK>(c));
-        IFL_TRY(launch_precon_backward(c, c->z, c->r, true, true)); // partial z.r
-        IFL_TRY(scalar_stage<SC_BETA>(c));
-        {
-            ProfScope ps_(c, IFL_K_XPAY);
-            k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
-            IFL_LAUNCHED(c);
-        }
-        return dist_barrier(c, true);
-    }
     {
         ProfScope ps_(c, IFL_K_AXPY2_NORM);
         k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, partials_next(c),
@@ -379,7 +366,9 @@ static int enqueue_iteration(ifl_ctx *c) {
 int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
     cudaStream_t st = c->stream;
     // prologue v3:350-358
-    IFL_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScalars), st));
+    // (the watchdog word is sticky: a factorisation sweep or a barrier that timed out BEFORE this
+    // solve must still be seen by the first read-back below)
+    IFL_CUDA(cudaMemsetAsync(c->scal, 0, offsetof(SolveScalars, watchdog), st));
     IFL_CUDA(cudaMemsetAsync((char *)c->p.p + c->p.own_begin(), 0, c->p.own_end() - c->p.own_begin(), st));
     IFL_TRY(dist_barrier(c, false)); // the upstream slab's last row of cy (factorisation) is final
     IFL_TRY(launch_precon_forward(c, c->z, c->r, false));
@@ -415,7 +404,8 @@ int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
         }
         last = c->scal_h[sl];
         if (last.watchdog) {
-            set_error("pcg_project: wavefront dependency watchdog fired");
+            set_error("pcg_project: a dependency wait (wavefront hand-off or rank barrier) timed out");
+            cudaMemsetAsync(&c->scal->watchdog, 0, sizeof(int), st);
             return IFL_E_WATCHDOG;
         }
         return IFL_OK;

@@ -1,6 +1,4 @@
-// sweep_common.cuh -- PTX helpers shared by the wavefront kernels (sweep_kernels.cu: MIC(0)
-// factorisation and Gauss-Seidel, one column per step; sweep2_kernels.cu: the two
-// triangular solves of the PCG loop, two columns per step).
+// sweep_common.cuh -- PTX helpers of the wavefront kernels (sweep_kernels.cu).
 #pragma once
 #include "ifl_internal.cuh"
 
@@ -8,11 +6,33 @@
 
 namespace ifl {
 
-constexpr unsigned WATCHDOG_POLLS = 1u << 23; // hand-off polls (each an L2 round trip); generous: with several ranks the
-                                              // upstream slab may start milliseconds later
-constexpr unsigned WATCHDOG_TRIES = 1u << 20; // mbarrier try_wait calls (each suspends for a while)
+// Every in-kernel dependency wait is bounded in TIME (%globaltimer), not in polls: a poll of a
+// shared-memory counter costs ~40 ns, an L2 / NVLink poll ~1 us and an mbarrier try_wait may
+// suspend for microseconds, so a poll count means nothing.  Two seconds is far beyond any legal
+// wait (with several ranks the upstream slab may start milliseconds later) and still returns the
+// GPU promptly when the protocol is broken or a peer has died.
+constexpr unsigned long long WATCHDOG_NS = 2000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin-loop bookkeeping: `n` counts polls, `t0` is latched on the first slow-path check; the
+// clock is read every 256 polls only, so the fast path stays two instructions long.
+struct Watch {
+    unsigned n;
+    unsigned long long t0;
+    __device__ __forceinline__ Watch() : n(0), t0(0) {}
+    __device__ __forceinline__ bool expired(volatile int *dead) {
+        if ((++n & 255u) != 0) return false;
+        if (*dead) return true;
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        return now - t0 > WATCHDOG_NS;
+    }
+};
 
-int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out);
+int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, int box_h, CUtensorMap *out);
 
 // ------------------------------------------------------------------ PTX helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -44,9 +64,9 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity, volatile int *dead, SolveScalars *scal) {
     if (mbar_try(bar, parity)) return;
     if (*dead) return;
-    unsigned n = 0;
+    Watch w;
     while (!mbar_try(bar, parity)) {
-        if (++n > WATCHDOG_TRIES || *dead) {
+        if (w.expired(dead)) {
             *dead = 1;
             scal->watchdog = 1;
             return;
@@ -182,9 +202,9 @@ __device__ __forceinline__ unsigned counter_load(uint32_t a) {
 template <bool ACQUIRE = false>
 __device__ __forceinline__ void wait_counter(uint32_t a, unsigned need, volatile int *dead, SolveScalars *scal) {
     if (counter_load<ACQUIRE>(a) >= need) return;
-    unsigned n = 0;
+    Watch w;
     while (counter_load<ACQUIRE>(a) < need) {
-        if (++n > WATCHDOG_POLLS || *dead) {
+        if (w.expired(dead)) {
             *dead = 1;
             scal->watchdog = 1;
             return;

@@ -32,7 +32,6 @@
 //       warp 2 (storer): drains finished result tiles smem -> HBM with 16-byte stores and folds
 //         dotProduct(z, r) for the backward solve.
 //       warp 3 (publisher) / warp 5 (poller): the strip-to-strip hand-off, below.
-//       (warp 6, KIND_FWD_AXPY only: streams p += alpha*s.)
 //     Stages are recycled through mbarriers (full / done / empty).
 //   * Strip-to-strip hand-off of the swept variable: NCCL-LL style 16-byte messages
 //     {lo, tag, hi, tag}, 8 columns at a time, validated by the consumer's poller warp and
@@ -55,17 +54,13 @@
 #endif
 
 #include <cuda.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
 namespace ifl {
 
-enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3, KIND_FACTOR_M = 4, KIND_FWD_AXPY = 5 }; // _M: with solid cells (v5:715-744)
-// KIND_FWD_AXPY: forward substitution fused with the two scaledAdds and the infinityNorm that precede it
-// in the PCG loop (v3:363-366): r += q*(-alpha) on the fly (tile 4 holds q = A*s and receives the new r),
-// |r|inf folded by the storer warp while it drains that tile, p += s*alpha streamed by a warp of its own.
-// The sweep is bound by its dependency chain and leaves ~85 % of the HBM bandwidth idle, so the 48 B/cell
-// of k_axpy2_norm ride along for free instead of costing a kernel of their own.
+enum { KIND_FWD = 0, KIND_BWD = 1, KIND_FACTOR = 2, KIND_GS = 3, KIND_FACTOR_M = 4 }; // _M: with solid cells (v5:715-744)
 
 // A tile is one TMA box: 33 rows x 32 doubles, dense (256-byte rows).  Forward kinds
 // fetch memory rows y0-1 .. y0+31 (tile row 0 = the upstream strip's last row, lane t
@@ -107,11 +102,10 @@ struct SweepParams {
     SolveScalars *scal;
     int gated;        // skip when scal->done
     double *partials; // KIND_BWD with dot: partial z.r per strip | KIND_GS: max |dp| per strip
-    double *p_upd;       // KIND_FWD_AXPY: p (updated by the p-updater warp)
-    const double *s_upd; // KIND_FWD_AXPY: s
     double scale;     // KIND_GS: timestep/(density*hx*hx)  v2:234
     int mask_tile;    // >= 0: results are stored only where this tile is non-zero (fluid cells), else -1
     int cs;           // thread-block cluster size (1 = no cluster): strips of one cluster hand off through DSMEM
+    int head_delay;   // SM cycles the head strip (no upstream neighbour) idles per macro-step, see sweep_init
     unsigned long long *times; // diagnostics: [nby][2] globaltimer ns at strip start / end (or null)
 };
 
@@ -150,12 +144,11 @@ __device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t p_right, uint
         o.b = lds_f64(p_right);            // p (old)  right cell
         o.c = lds_f64(p + 1 * TILE_BYTES); // p (old)  lower cell (tile 1 = p fetched one row down)
         o.d = lds_f64(p + 2 * TILE_BYTES); // r        own cell
-    } else if (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) {
+    } else if (KIND == KIND_FWD) {
         o.a = lds_f64(p);                       // a (rhs)  own cell
         o.b = lds_f64(p + 1 * TILE_BYTES);      // cx       own cell (carried to the next step)
         o.c = lds_f64(p + 2 * TILE_BYTES + UP); // cy       upper cell
         o.d = lds_f64(p + 3 * TILE_BYTES);      // precon   own cell
-        if (KIND == KIND_FWD_AXPY) o.e = lds_f64(p + 4 * TILE_BYTES); // q = A*s own cell
     } else if (KIND == KIND_BWD) {
         o.a = lds_f64(p);                            // z (forward result) own cell, updated in place
         o.b = lds_f64(p + 1 * TILE_BYTES);           // cx own
@@ -181,7 +174,6 @@ struct GsConst {
     int W;
     int ncols;             // padded sweep width (32 * nbx)
     int cluster;           // hand-off counter is bumped remotely (DSMEM): needs acquire loads
-    double nalpha;         // KIND_FWD_AXPY: -alpha of this PCG iteration (v3:364)
 };
 
 // One cell.  `up` is the swept variable of the upper (upstream-row) neighbour, `c` the
@@ -218,13 +210,8 @@ __device__ __forceinline__ double cell(const Ops &o, Carry &cr, double up, uint3
         znew = (o.d - off) / diag;       // v2:267
         if (gs.yvalid && c < gs.W && (ALWAYS || active)) cr.acc = std_max(cr.acc, fabs(o.a - znew)); // v2:269
         sts_f64_p<ALWAYS>(p, znew, active); // v2:271
-    } else if (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) {
-        double rhs = o.a;
-        if (KIND == KIND_FWD_AXPY) {
-            rhs = o.a + o.e * gs.nalpha;                         // v3:364  r[i] = r[i] + z[i]*(-alpha)   (z holds A*s)
-            sts_f64_p<ALWAYS>(p + 4 * TILE_BYTES, rhs, active); // the q tile becomes the new r
-        }
-        double t = rhs - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
+    } else if (KIND == KIND_FWD) {
+        double t = o.a - cr.c1 * cr.zprev; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
         t = t - o.c * up;                  // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
         znew = t * o.d;                    // v3:285
         sts_f64_p<ALWAYS>(p, znew, active); // in place: the rhs tile becomes the result tile
@@ -367,7 +354,6 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
         gs.W = P.W;
         gs.ncols = P.nbx * 32;
         gs.cluster = 0; // the hand-off counter is always bumped by this CTA's own poller warp
-        gs.nalpha = (KIND == KIND_FWD_AXPY) ? -P.scal->alpha : 0.0;
     }
     Ops ops;
     ops.a = ops.b = ops.c = ops.d = ops.e = ops.f = ops.halo = 0.0;
@@ -395,6 +381,10 @@ __device__ void compute_warp(const SweepParams &P, double *smem, double *halo_s,
             P.times[16 * sj + 2 + m / ck] = tt;
         }
 #endif
+        if (!has_up && P.head_delay > 0) { // pace-setter: see sweep_init
+            const long long t_ = clock64();
+            while (clock64() - t_ < P.head_delay) {}
+        }
         const bool has_next = m + 1 < nbx;
         const uint32_t s_prev = row0 + sp * stage_bytes;
         const uint32_t s_cur = row0 + sc * stage_bytes;
@@ -487,7 +477,7 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
     const uint4 *up_row = P.handoff + (size_t)(sj - 1) * nbx * 32;
     const bool remote = sj == P.sj_base; // the upstream strip belongs to another rank
     const uint32_t progress_addr = smem_u32(&counters[0]), halo_cols_addr = smem_u32(&counters[1]);
-    unsigned polls = 0;
+    Watch watch;
     for (int m = 0; m < nbx; m++) {
         const int st = m % HR;
         if (m >= HR) wait_counter(progress_addr, (unsigned)(32 * (m - HR + 1)), dead, P.scal);
@@ -511,8 +501,8 @@ __device__ void poller_warp(const SweepParams &P, double *halo_s, int sj, int la
                 if (ok) {
                     halo_s[st * 32 + G::tcol(lane)] = v;
                     have = true;
-                    polls = 0;
-                } else if (++polls > WATCHDOG_POLLS || *dead) {
+                    watch = Watch();
+                } else if (watch.expired(dead)) {
                     *dead = 1;
                     P.scal->watchdog = 1;
                     have = true;
@@ -552,7 +542,6 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
     const int half = lane >> 4, l16 = lane & 15;
     const int toff = (G::BWD ? half : 1 + half) * TP + l16 * 2; // this lane's first element inside a tile
     double acc = 0.0;
-    double nrm = 0.0; // KIND_FWD_AXPY: max |r| over this lane's cells (v3:366)
     for (int m = 0; m < P.nbx; m++) {
         const int st = m % nst;
         const double *stage = smem + st * stage_doubles;
@@ -575,15 +564,8 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
                     acc += v[i].y * rv.y;
                 }
             }
-            if (KIND == KIND_FWD_AXPY && k == 4) { // the new r: fold infinityNorm (pad cells hold +0.0)
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    nrm = std_max(nrm, fabs(v[i].x));
-                    nrm = std_max(nrm, fabs(v[i].y));
-                }
-            }
             double *g = P.t[k].p + x + (size_t)(y0 + half) * P.pitch;
-            if (!MASKED || KIND == KIND_FACTOR_M || (KIND == KIND_FWD_AXPY && k == 4)) { // (r is a plain vector: never masked)
+            if (!MASKED || KIND == KIND_FACTOR_M) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     double *dst = g + (size_t)(i * 2) * P.pitch;
@@ -626,40 +608,6 @@ __device__ void storer_warp(const SweepParams &P, double *smem, uint64_t *done, 
         const double sum = warp_sum(acc);
         if (lane == 0) P.partials[sj] = sum;
     }
-    if (KIND == KIND_FWD_AXPY) {
-        const double mx = warp_max(nrm);
-        if (lane == 0) P.partials[sj] = mx;
-    }
-}
-
-// ------------------------------------------------------------------ p-updater ----
-// KIND_FWD_AXPY: p += s*alpha (v3:363) over the strip's 32 rows, a plain HBM stream that has
-// nothing to do with the wavefront; it lives in a warp of its own so that it never delays the
-// ring (the sweep leaves most of the HBM bandwidth idle anyway).
-__device__ void p_update_warp(const SweepParams &P, int sj, int lane) {
-    const double alpha = P.scal->alpha;
-    const int y0 = sj * 32, y1 = imin(y0 + 32, P.H);
-    const int npairs = P.pitch / 2; // pad columns hold zeros on both sides: p stays zero there
-    for (int y = y0; y < y1; y++) {
-        double2 *pr = reinterpret_cast<double2 *>(P.p_upd + (size_t)y * P.pitch);
-        const double2 *sr = reinterpret_cast<const double2 *>(P.s_upd + (size_t)y * P.pitch);
-        for (int i0 = 0; i0 < npairs; i0 += 128) {
-            double2 pv[4], sv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                if (i < npairs) {
-                    pv[u] = pr[i];
-                    sv[u] = sr[i];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * 32 + lane;
-                if (i < npairs) pr[i] = make_double2(pv[u].x + sv[u].x * alpha, pv[u].y + sv[u].y * alpha);
-            }
-        }
-    }
 }
 
 // -------------------------------------------------------------- publisher warp ----
@@ -692,7 +640,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
     int blk = 0;         // block `sent` lies in
     int st = 0;          // its stage
     const double *row = last_row;
-    unsigned n = 0;
+    Watch watch;
     while (sent < ncols) {
         const int prog = (int)lds_u32_volatile(progress_addr);
         if (prog > sent) {
@@ -705,7 +653,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
                     // left block blk - HR (its lane 0 is further ahead still)
                     while (blk >= HR && down_progress < 32 * (blk - HR + 1)) {
                         down_progress = (int)ld_remote_u32(r_progress);
-                        if (++n > WATCHDOG_POLLS || *dead) {
+                        if (watch.expired(dead)) {
                             *dead = 1;
                             P.scal->watchdog = 1;
                             break;
@@ -741,8 +689,8 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
             }
             if (P.times && lane == 0 && prog == (P.nbx / 2) * 32)
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(P.times[16 * sj + 12]));
-            n = 0;
-        } else if (++n > WATCHDOG_POLLS || ((n & 63u) == 0 && *dead)) {
+            watch = Watch();
+        } else if (watch.expired(dead)) {
             *dead = 1;
             P.scal->watchdog = 1;
             // release every stage so that the other warps can finish
@@ -755,7 +703,7 @@ __device__ void publisher_warp(const SweepParams &P, double *smem, double *halo_
 
 // ---------------------------------------------------------------------- kernel ----
 template <int KIND, bool DOT, bool MASKED>
-__global__ void __launch_bounds__(224, 1) k_sweep(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(192, 1) k_sweep(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[3 * MAX_STAGES]; // full[], done[], empty[]
     __shared__ int s_ticket;
@@ -822,8 +770,6 @@ __global__ void __launch_bounds__(224, 1) k_sweep(const __grid_constant__ SweepP
         storer_warp<KIND, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
     } else if (warp == 3) {
         if (sj + 1 < P.nby) publisher_warp<KIND>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank);
-    } else if (warp == 6) {
-        if (KIND == KIND_FWD_AXPY) p_update_warp(P, sj, lane);
     } else if (warp == 5 && sj > 0) {
         // (warp 4 stays idle: it would share the compute warp's scheduler, and a spinning
         // neighbour costs the recurrence ~12 cycles per step, profiles/microbench/step.cu)
@@ -850,21 +796,21 @@ static PFN_encodeTiled encode_fn() {
     return fn;
 }
 
-// Tensor map of one pitched cell array: 2-D, double, box = box_w columns x 33 rows, no
+// Tensor map of one pitched cell array: 2-D, double, box = box_w columns x box_h rows, no
 // swizzle (the skewed access pattern is conflict-free on dense rows), zero OOB fill.
 // Maps are cached per base pointer (flip() only swaps pointers).
 struct MapCache {
-    enum { N = 64 };
+    enum { N = 96 };
     void *key[N];
-    int box_w[N];
+    int box_w[N], box_h[N];
     CUtensorMap map[N];
     int n;
 };
 
-int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
+int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, int box_h, CUtensorMap *out) {
     MapCache *mc = (MapCache *)c->map_cache;
     for (int i = 0; i < mc->n; i++)
-        if (mc->key[i] == a.p && mc->box_w[i] == box_w) {
+        if (mc->key[i] == a.p && mc->box_w[i] == box_w && mc->box_h[i] == box_h) {
             *out = mc->map[i];
             return IFL_OK;
         }
@@ -875,7 +821,7 @@ int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)a.pitch, (cuuint64_t)a.rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)a.pitch * sizeof(double)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_w, 33u};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.p, gdim, gstride, box, estr,
@@ -888,42 +834,7 @@ int sweep_get_map(ifl_ctx *c, const Arr &a, int box_w, CUtensorMap *out) {
     if (mc->n < MapCache::N) {
         mc->key[mc->n] = a.p;
         mc->box_w[mc->n] = box_w;
-        mc->map[mc->n] = m;
-        mc->n++;
-    }
-    *out = m;
-    return IFL_OK;
-}
-
-// Store map of one pitched cell array for the one-warp engine (sweep3_kernels.cu): 32 x 32
-// boxes; the global extent is the LOGICAL w x h, so the hardware clips pad columns / rows.
-int sweep_get_store_map(ifl_ctx *c, const Arr &a, CUtensorMap *out) {
-    MapCache *mc = (MapCache *)c->map_cache;
-    for (int i = 0; i < mc->n; i++)
-        if (mc->key[i] == a.p && mc->box_w[i] == -32) {
-            *out = mc->map[i];
-            return IFL_OK;
-        }
-    PFN_encodeTiled enc = encode_fn();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return IFL_E_CUDA;
-    }
-    const cuuint64_t gdim[2] = {(cuuint64_t)a.w, (cuuint64_t)a.h};
-    const cuuint64_t gstride[1] = {(cuuint64_t)a.pitch * sizeof(double)};
-    const cuuint32_t box[2] = {32u, 32u};
-    const cuuint32_t estr[2] = {1, 1};
-    CUtensorMap m;
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.p, gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (store map) failed (%d) for a %dx%d array", (int)r, a.w, a.h);
-        return IFL_E_CUDA;
-    }
-    if (mc->n < MapCache::N) {
-        mc->key[mc->n] = a.p;
-        mc->box_w[mc->n] = -32;
+        mc->box_h[mc->n] = box_h;
         mc->map[mc->n] = m;
         mc->n++;
     }
@@ -959,27 +870,22 @@ int sweep_init(ifl_ctx *c) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
     }
-    // IFL_SWEEP_V2=1 selects the two-columns-per-step kernels (sweep2_kernels.cu) for the
-    // triangular solves: bit-exact, but measured slower at 4096^2 (855 vs 702 us per sweep),
-    // so the one-column engine of this file stays the default.
-    c->sweep_v2 = 0;
-    if (const char *e = getenv("IFL_SWEEP_V2"))
-        if (atoi(e) == 1 && c->world == 1) c->sweep_v2 = 1;
-    // IFL_SWEEP_V3=1 selects the one-warp-per-CTA engine (sweep3_kernels.cu) for the triangular
-    // solves of chapters 1-3: bit-exact, predicted 77 cycles per step by the microbenchmark but
-    // measured 100 (688 us per 4096^2 sweep against 645 us here) once real TMA traffic shares the
-    // shared-memory pipe with the shuffles; kept for A/B measurements.
-    c->sweep_v3 = 0;
-    if (const char *e = getenv("IFL_SWEEP_V3"))
-        if (atoi(e) == 1 && c->version <= 3 && !c->sweep_v2) c->sweep_v3 = 1;
-    // IFL_FUSE_AXPY=1 (chapters 3-5: plain, unmasked vector helpers) fuses v3:363-366 into the
-    // forward sweep (KIND_FWD_AXPY).  Bit-exact, but OFF by default: at 4096^2 the fused sweep
-    // takes 0.746 ms against 0.567 + 0.125 ms for the sweep and k_axpy2_norm on their own -- one
-    // more operand load, store and two FP64 ops per step in the in-order compute warp, a fifth
-    // tile in the TMA ring and a streaming warp next to it cost more than the kernel they save.
-    c->fuse_axpy = 0;
-    if (const char *e = getenv("IFL_FUSE_AXPY"))
-        if (atoi(e) == 1 && c->version >= 3 && c->version <= 5 && !c->sweep_v2 && !c->sweep_v3) c->fuse_axpy = 1;
+    // Every strip with an upstream neighbour runs at the same pace (the hand-off checks make it ~3 %
+    // slower than the head strip), so the lag a strip picks up while it starts -- cold instruction
+    // cache, first TMA tiles, first hand-off -- is frozen for the whole sweep: a consumer that is not
+    // faster than its producer never catches up (profiles/r01_g_sweep_timeline_4096.txt: 2.9 us per
+    // strip, of which the hand-off itself explains ~2.1).  Letting the head strip idle a few cycles
+    // per macro-step makes IT the pace-setter; all others then run into their hand-off waits and
+    // settle at the minimal lag (skew + group + hand-off latency).  IFL_SWEEP_HEAD_DELAY overrides.
+    c->sweep_head_delay = 0;
+    if (const char *e = getenv("IFL_SWEEP_HEAD_DELAY")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 100000) c->sweep_head_delay = v;
+    }
+    // The triangular solves of the PCG loop run on the two-rows-per-lane engine (tri_kernels.cu);
+    // IFL_TRI=0 keeps them on this file's one-row engine for A/B measurements.
+    c->tri_engine = 1;
+    if (const char *e = getenv("IFL_TRI")) c->tri_engine = atoi(e) != 0;
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -1015,7 +921,7 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
         P.t[k].store = spec[k].store;
         P.t[k].p2 = spec[k].a2 ? spec[k].a2->p : nullptr;
         if (spec[k].load) {
-            int rc = sweep_get_map(c, *spec[k].a, 32, &P.map[k]);
+            int rc = sweep_get_map(c, *spec[k].a, 32, TROWS, &P.map[k]);
             if (rc != IFL_OK) return rc;
         }
     }
@@ -1044,10 +950,11 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
     c->sweep_tickets += (unsigned long long)n_clusters;
     c->sweep_launches++;
     P.scal = c->scal;
+    P.head_delay = c->sweep_head_delay;
     P.times = c->sweep_times;
     const size_t smem = (size_t)nst * nt * TILE_BYTES + (size_t)HR * 32 * sizeof(double) + (P.cs > 1 ? (size_t)HR * 32 * sizeof(uint4) : 0);
     const bool masked = P.mask_tile >= 0;
-    static bool attr_set[IFL_MAX_DEVICES][6][2][2]; // function attributes are per device
+    static bool attr_set[IFL_MAX_DEVICES][5][2][2]; // function attributes are per device
     if (!attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked]) {
         IFL_CUDA(masked ? cudaFuncSetAttribute(k_sweep<KIND, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                227 * 1024 - 1024)
@@ -1057,11 +964,11 @@ static int launch_sweep(ifl_ctx *c, SweepParams &P, const TileSpec *spec, int nt
                         : cudaFuncSetAttribute(k_sweep<KIND, DOT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[c->device % IFL_MAX_DEVICES][KIND][DOT][masked] = true;
     }
-    ProfScope ps_(c, (KIND == KIND_FWD || KIND == KIND_FWD_AXPY) ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
+    ProfScope ps_(c, KIND == KIND_FWD ? IFL_K_PRECON_FWD : KIND == KIND_BWD ? IFL_K_PRECON_BWD : (KIND == KIND_FACTOR || KIND == KIND_FACTOR_M) ? IFL_K_FACTOR : IFL_K_GS_SWEEP);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
-    cfg.blockDim = dim3(KIND == KIND_FWD_AXPY ? 224 : 192); // + the p-updater warp
+    cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -1114,8 +1021,7 @@ static int solve_stages(ifl_ctx *c) {
 }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
-    if (c->sweep_v3) return launch_precon_forward3(c, dst, a, gated);
-    if (c->sweep_v2) return launch_precon_forward2(c, dst, a, gated);
+    if (c->tri_engine) return launch_tri_forward(c, dst, a, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
@@ -1128,28 +1034,8 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
     return launch_sweep<KIND_FWD, false>(c, P, spec, 4, solve_stages(c));
 }
 
-// One launch for v3:363-366 + the forward half of v3:372: p += alpha*s, r -= alpha*q, |r|inf
-// (-> partials) and z = forward substitution of the NEW r.  alpha is read from scal->alpha.
-int launch_precon_forward_axpy(ifl_ctx *c) {
-    SweepParams P;
-    memset(&P, 0, sizeof P);
-    P.gated = 1;
-    P.mask_tile = c->version >= 4 ? 3 : -1;
-    const TileSpec spec[5] = {{&c->r, 1, 0, 1, nullptr, &c->z},
-                              {&c->cx, 1, 0, 0, nullptr, nullptr},
-                              {&c->cy, 1, 0, 0, nullptr, nullptr},
-                              {&precon_operand(c), 1, 0, 0, nullptr, nullptr},
-                              {&c->q, 1, 0, 1, nullptr, &c->r}};
-    P.p_upd = c->p.p;
-    P.s_upd = c->s.p;
-    P.partials = partials_next(c);
-    c->n_partials = (c->H + 31) / 32;
-    return launch_sweep<KIND_FWD_AXPY, false>(c, P, spec, 5, solve_stages(c));
-}
-
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
-    if (c->sweep_v3) return launch_precon_backward3(c, dst, r_for_dot, with_dot, gated);
-    if (c->sweep_v2) return launch_precon_backward2(c, dst, r_for_dot, with_dot, gated);
+    if (c->tri_engine) return launch_tri_backward(c, dst, r_for_dot, with_dot, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
     P.gated = gated ? 1 : 0;
@@ -1206,7 +1092,7 @@ static int enqueue_gs_sweep(ifl_ctx *c, double scale) {
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info) {
     cudaStream_t st = c->stream;
     const double scale = timestep / (density * c->hx * c->hx); // v2:234
-    IFL_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScalars), st));
+    IFL_CUDA(cudaMemsetAsync(c->scal, 0, offsetof(SolveScalars, watchdog), st)); // the watchdog word is sticky
     cudaEvent_t ev[2];
     IFL_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     IFL_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
@@ -1239,7 +1125,8 @@ int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve
         head ^= 1;
         pending--;
         if (last.watchdog) {
-            set_error("gs_project: wavefront dependency watchdog fired");
+            set_error("gs_project: a dependency wait (wavefront hand-off or rank barrier) timed out");
+            cudaMemsetAsync(&c->scal->watchdog, 0, sizeof(int), st);
             rc = IFL_E_WATCHDOG;
         }
     }

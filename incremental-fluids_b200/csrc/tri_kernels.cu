@@ -1,0 +1,638 @@
+// tri_kernels.cu -- the two triangular solves of FluidSolver::applyPreconditioner
+// (v3:275-304; masked form v5:746-780), round-2 engine: TWO rows per lane.
+//
+//   forward   t = a[i] - cx[i-1]*z[i-1] - cy[i-w]*z[i-w] ; z[i] = t*precon[i]     v3:276-287
+//   backward  t = z[i] - cx[i]*z[i+1]   - cy[i]*z[i+w]   ; z[i] = t*precon[i]     v3:289-303
+//             (+ dotProduct(z, r) of v3:374 folded in by the storer warp)
+//   cx = aPlusX*precon, cy = aPlusY*precon are written by the factorisation (sweep_kernels.cu);
+//   the reference evaluates `_aPlusX[i]*_precon[i]*dst[i]` left to right (v3:281), so this is the
+//   same product.  Any schedule that honours the (x-1,y),(x,y-1) dependencies performs the same
+//   floating-point operations on the same operands as the raster loop: results are bit-identical.
+//
+// Why a second engine (the one-row engine of sweep_kernels.cu still runs the factorisation and
+// Gauss-Seidel): a sweep is a wave that has to cross W + H cells; its duration is
+//     (W + strips * (skew + hand-off)) * T_step.
+// The one-row engine (32-row strips) measured T = 87 cycles and 66 steps of lag per strip at 4096^2.
+// Here a lane owns two vertically adjacent rows: cell A (upper row) takes its upper neighbour from
+// the lane above by shuffle, as before, and cell B (lower row) takes A straight from a register.
+// A step is longer (one more mul-sub-mul chain) but a strip is 64 rows tall: half the strips, half
+// the hand-offs, half the skew steps, and the per-step overheads (hand-off polling, ring barriers,
+// address selects) are paid once for two rows.
+//
+// Geometry
+//   * strip = 64 rows, one CTA (1 per SM); lane t owns tile rows 1+2t, 2+2t (forward; tile row 0 is
+//     the upstream strip's last row) or 63-2t, 62-2t (backward; tile row 64 is the upstream row) and
+//     runs one column behind lane t-1: the warp is an anti-diagonal, 31 columns long.
+//   * operands are staged by TMA in blocks of 16 columns x 65 rows (one box per operand per block:
+//     rhs/z, cx, cy, precon), 6-stage ring.  Lanes 0..15 work in blocks m-1 and m, lanes 16..31 in
+//     m-2 and m-1; a block is released when lane 31 has left it.  Rows are dense (128 bytes), lane t
+//     reads column (k - t) mod 16: the 16 lanes of a half-warp hit 16 different 8-byte bank slots.
+//   * warps: 0 compute, 1 TMA loader, 2 storer (drains z, folds z.r reading r straight from global
+//     memory -- it does not depend on the sweep, so its loads are issued before the wait), 3 publisher,
+//     5 poller (strip-to-strip hand-off, same protocol as sweep_kernels.cu: LL messages through the
+//     downstream CTA's shared memory inside a thread-block cluster, through L2 / NVLink otherwise).
+#include "ifl_internal.cuh"
+#include "sweep_common.cuh"
+
+#include <cuda.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+// Timing experiments (profiles/tri_experiments.sh builds one library per value; never set in the
+// product build): bit 0 no fence.proxy.async in the compute warp, bit 1 no ring barriers at all (the
+// compute warp runs over whatever is in shared memory: garbage results, pure step time), bit 2 no
+// progress stores, bit 3 no lane-0 hand-off select.
+#ifndef TRI_EXP
+#define TRI_EXP 0
+#endif
+
+namespace ifl {
+namespace tri {
+
+constexpr int SR = 64;                        // rows per strip
+constexpr int BW = 16;                        // columns per block
+constexpr int TROWS = SR + 1;                 // tile rows (one upstream row)
+constexpr int ROWB = BW * 8;                  // bytes per tile row
+constexpr int TILE_BYTES = TROWS * ROWB;      // 8320 (multiple of 128)
+constexpr int NT = 4;                         // tiles per stage: rhs/z, cx, cy, precon
+constexpr int STAGE_BYTES = NT * TILE_BYTES;  // 33280
+constexpr int NST = 6;                        // ring depth
+constexpr int HG = 8;                         // hand-off granularity (columns)
+constexpr int HRC = 512;                      // hand-off ring (columns): deep enough that back-pressure never binds
+
+struct TriParams {
+    CUtensorMap map[NT]; // must stay first (64-byte aligned)
+    double *dst;         // z: receives the swept tile
+    const double *rdot;  // backward + dot: r
+    int W, H, pitch, nbx, nby; // nbx blocks of 16 columns, nby strips of 64 rows
+    uint4 *handoff;      // [nby][ncols] LL messages between strips of different clusters
+    int sj_base, nloc;   // this rank's strips, in sweep order
+    uint4 *handoff_down; // hand-off array of the downstream rank
+    unsigned epoch;
+    unsigned long long *ticket;
+    unsigned long long ticket_base;
+    SolveScalars *scal;
+    int gated;
+    double *partials; // z.r per strip
+    int cs;           // cluster size
+    int head_delay;
+    unsigned long long *times;
+};
+
+template <bool BWD>
+struct Geo {
+    static constexpr int DIR = BWD ? -8 : 8;       // bytes per logical column
+    static constexpr int COL0 = BWD ? BW - 1 : 0;  // tile column of logical in-block column 0
+    static constexpr int ROW_B = BWD ? -ROWB : ROWB; // cell A -> cell B (same column)
+    static constexpr int UP_CY = BWD ? 0 : -ROWB;  // own cell -> the cell whose cy multiplies the upstream value
+    __device__ static __forceinline__ int row_a(int lane) { return BWD ? SR - 1 - 2 * lane : 1 + 2 * lane; }
+    __device__ static __forceinline__ int last_row() { return BWD ? 0 : SR; } // tile row of the strip's last row
+    __device__ static __forceinline__ int tcol(int ci) { return BWD ? BW - 1 - ci : ci; }
+};
+
+struct Carry {
+    double zA, zB; // swept variable of the previous column
+    double cA, cB; // forward: cx of the previous column
+};
+struct Ops {
+    double aA, xA, yA, pA, aB, xB, yB, pB, halo;
+};
+
+template <bool BWD>
+__device__ __forceinline__ void fetch(Ops &o, uint32_t p, uint32_t ph) {
+    typedef Geo<BWD> G;
+    const uint32_t pb = p + (uint32_t)G::ROW_B;
+    o.aA = lds_f64(p);
+    o.xA = lds_f64(p + TILE_BYTES);
+    o.yA = lds_f64(p + 2 * TILE_BYTES + (uint32_t)G::UP_CY);
+    o.pA = lds_f64(p + 3 * TILE_BYTES);
+    o.aB = lds_f64(pb);
+    o.xB = lds_f64(pb + TILE_BYTES);
+    o.yB = lds_f64(pb + 2 * TILE_BYTES + (uint32_t)G::UP_CY);
+    o.pB = lds_f64(pb + 3 * TILE_BYTES);
+    o.halo = lds_f64(ph); // same address in every lane (broadcast); only lane 0 uses it
+}
+
+// Per-lane tile-0 base pointers of one macro-step (16 steps).  With r = lane & 15 the lane moves
+// from its "before" block into its "after" block at step kk == r; the address of logical step j is
+// always `selected base + DIR*j`, j a compile-time constant.  N serves the look-ahead fetch (j == 16)
+// of the lanes with r == 0.
+struct LaneBases {
+    uint32_t A, B, N;
+};
+template <bool BWD>
+__device__ __forceinline__ uint32_t pos(const LaneBases &lb, int j, int r) {
+    uint32_t base = (r > j) ? lb.B : lb.A;
+    if (j >= BW) base = (r == 0) ? lb.N : lb.A;
+    return base + (uint32_t)(Geo<BWD>::DIR * j);
+}
+
+// EDGE 0: every lane is inside the strip.  EDGE 1: first two macro-steps (lanes enter one by one),
+// EDGE 2: last two (lanes leave).  Lanes outside run the same instructions on aliased operands with
+// their stores predicated off; what they compute is never consumed (lane t-1 is inside at step k-1
+// exactly when lane t is inside at step k).
+template <bool BWD, int EDGE>
+__device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next, uint64_t *full_next,
+                                           unsigned parity_next, bool wait_next, int m, int lane, int r, Carry &cr, Ops &ops,
+                                           uint32_t progress_addr, uint32_t gate_addr, bool has_up, int ncols,
+                                           volatile int *dead, SolveScalars *scal) {
+    typedef Geo<BWD> G;
+    uint32_t p = pos<BWD>(lb, 0, r);
+    unsigned gate_seen = 0;
+#pragma unroll
+    for (int kk = 0; kk < BW; kk++) {
+        if (kk == BW - 1 && wait_next && !(TRI_EXP & 2)) mbar_wait(full_next, parity_next, dead, scal); // lanes 0/16 are about to touch the next block
+        // hand-off gate: read four steps early, tested when lane 0 is about to need the next group
+        if (((kk + 5) % HG) == 0 && has_up && EDGE != 2) gate_seen = lds_u32_volatile(gate_addr);
+        if (((kk + 1) % HG) == 0 && has_up && EDGE != 2) {
+            const unsigned need = (unsigned)imin(BW * m + kk + 1 + HG, ncols);
+            if (gate_seen < need) wait_counter<false>(gate_addr, need, dead, scal);
+        }
+        // ---- critical path first: the upstream lane's B of the previous step
+        double up = __shfl_up_sync(0xffffffffu, cr.zB, 1);
+        // ---- operands of step kk+1, in the shadow of the shuffle
+        Ops nxt;
+        const uint32_t pn = pos<BWD>(lb, kk + 1, r);
+        const uint32_t ph = (kk + 1 < BW) ? h_cur + (uint32_t)(8 * (kk + 1)) : h_next;
+        fetch<BWD>(nxt, pn, ph);
+        // ---- this step
+        const int c = BW * m + kk - lane; // logical column of this lane
+        const bool active = (EDGE == 0) ? true : (EDGE == 1 ? c >= 0 : c < ncols);
+        if (EDGE == 1) {
+            const bool first = c == 0;
+            cr.zA = sel_f64(first, 0.0, cr.zA);
+            cr.zB = sel_f64(first, 0.0, cr.zB);
+            if (!BWD) {
+                cr.cA = sel_f64(first, 0.0, cr.cA);
+                cr.cB = sel_f64(first, 0.0, cr.cB);
+            }
+        }
+        if (!(TRI_EXP & 8)) up = sel_f64(lane == 0, ops.halo, up);
+        double zA, zB;
+        if (!BWD) {
+            double t = ops.aA - cr.cA * cr.zA; // v3:281  t -= aPlusX[idx-1]*precon[idx-1]*dst[idx-1]
+            t = t - ops.yA * up;               // v3:283  t -= aPlusY[idx-w]*precon[idx-w]*dst[idx-w]
+            zA = t * ops.pA;                   // v3:285
+            double u = ops.aB - cr.cB * cr.zB;
+            u = u - ops.yB * zA; // the row above B is A
+            zB = u * ops.pB;
+            cr.cA = ops.xA;
+            cr.cB = ops.xB;
+        } else {
+            double t = ops.aA - ops.xA * cr.zA; // v3:297  t -= aPlusX[idx]*precon[idx]*dst[idx+1]
+            t = t - ops.yA * up;                // v3:299  t -= aPlusY[idx]*precon[idx]*dst[idx+w]
+            zA = t * ops.pA;                    // v3:301
+            double u = ops.aB - ops.xB * cr.zB;
+            u = u - ops.yB * zA; // the row below B is A
+            zB = u * ops.pB;
+        }
+        sts_f64_p<EDGE == 0>(p, zA, active); // in place: the rhs / z tile becomes the result tile
+        sts_f64_p<EDGE == 0>(p + (uint32_t)G::ROW_B, zB, active);
+        cr.zA = zA;
+        cr.zB = zB;
+        // the strip's last row (lane 31, cell B) has just completed another group of HG columns
+        if (((kk + 2) % HG) == 0 && !(TRI_EXP & 4)) sts_u32_volatile(progress_addr, (unsigned)imin(imax(BW * m + kk - 30, 0), ncols));
+        ops = nxt;
+        p = pn;
+    }
+}
+
+template <bool BWD>
+__device__ void compute_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *full, uint64_t *done, int sj,
+                             int lane, volatile int *dead, unsigned *counters) {
+    typedef Geo<BWD> G;
+    Carry cr;
+    cr.zA = cr.zB = cr.cA = cr.cB = 0.0;
+    const bool has_up = sj > 0 && !(TRI_EXP & 2);
+    const uint32_t progress_addr = smem_u32(&counters[0]), gate_addr = smem_u32(&counters[1]);
+    const int nbx = P.nbx, ncols = P.nbx * BW;
+    const int q = lane >> 4, r = lane & 15;
+    // this lane's row A in tile 0 of stage 0 at logical in-block column 0
+    const uint32_t row0 = smem_u32(smem) + (uint32_t)(G::row_a(lane) * ROWB + G::COL0 * 8);
+    const uint32_t halo0 = smem_u32(halo_s);
+    // blocks of a lane in macro-step m: after its transition (bA = m - q), before (bA - 1), look-ahead of the
+    // r == 0 lanes (bA + 1); blocks outside [0, nbx) are only touched by lanes outside the strip and alias
+    // valid memory
+    auto bases = [&](int m) {
+        const int bA = m - q;
+        const int sA = imin(imax(bA, 0), nbx - 1) % NST;
+        const int sB = imin(imax(bA - 1, 0), nbx - 1) % NST;
+        const int sN = imin(imax(bA + 1, 0), nbx - 1) % NST;
+        LaneBases lb;
+        lb.A = row0 + (uint32_t)(sA * STAGE_BYTES) - (uint32_t)(G::DIR * r);
+        lb.B = row0 + (uint32_t)(sB * STAGE_BYTES) + (uint32_t)(G::DIR * (BW - r));
+        lb.N = row0 + (uint32_t)(sN * STAGE_BYTES) - (uint32_t)(G::DIR * BW);
+        return lb;
+    };
+    Ops ops;
+    // everything that does not depend on the upstream strip happens BEFORE the wait for its first
+    // hand-off group: that wait sits on the critical path of the whole sweep
+    if (!(TRI_EXP & 2)) mbar_wait(&full[0], 0, dead, P.scal);
+    fetch<BWD>(ops, pos<BWD>(bases(0), 0, r), halo0); // step 0: lane 0 at column 0, the others idle on valid memory
+    if (has_up) {
+        wait_counter<false>(gate_addr, (unsigned)imin(HG, ncols), dead, P.scal);
+        ops.halo = lds_f64(halo0);
+    }
+    const int nm = nbx + 2; // macro-steps: lane 31 finishes column ncols-1 at step ncols + 30
+    for (int m = 0; m < nm; m++) {
+        if (!has_up && P.head_delay > 0) { // pace-setter, see sweep_init
+            const long long t_ = clock64();
+            while (clock64() - t_ < P.head_delay) {}
+        }
+        const LaneBases lb = bases(m);
+        const uint32_t h_cur = halo0 + (uint32_t)(((BW * m) % HRC) * 8);
+        const uint32_t h_next = halo0 + (uint32_t)(((BW * (m + 1)) % HRC) * 8);
+        const bool wait_next = m + 1 < nbx; // block m+1 exists: lane 0 steps into it at the look-ahead
+        uint64_t *full_next = &full[(m + 1) % NST];
+        const unsigned parity_next = (unsigned)(((m + 1) / NST) & 1);
+        if (m < 2)
+            macro_step<BWD, 1>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
+                               has_up, ncols, dead, P.scal);
+        else if (m >= nbx)
+            macro_step<BWD, 2>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
+                               has_up, ncols, dead, P.scal);
+        else
+            macro_step<BWD, 0>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
+                               has_up, ncols, dead, P.scal);
+        if (m >= 2 && !(TRI_EXP & 2)) { // lane 31 has left block m-2: hand it to the storer (and, through it, the loader)
+            if (!(TRI_EXP & 1)) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[(m - 2) % NST]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------- loader warp ----
+template <bool BWD>
+__device__ void loader_warp(const TriParams &P, unsigned char *smem, uint64_t *full, uint64_t *empty, int sj, int lane,
+                            volatile int *dead) {
+    if (lane != 0) return;
+    const int nbx = P.nbx;
+    const int ty = BWD ? (P.nby - 1 - sj) : sj; // memory strip of this CTA
+    const int box_y = BWD ? ty * SR : ty * SR - 1;
+    for (int b = 0; b < nbx; b++) {
+        const int st = b % NST;
+        if (b >= NST) mbar_wait(&empty[st], (unsigned)(((b / NST) - 1) & 1), dead, P.scal);
+        mbar_arrive_expect_tx(&full[st], (unsigned)STAGE_BYTES);
+        const int box_x = (BWD ? (nbx - 1 - b) : b) * BW;
+        unsigned char *stage = smem + (size_t)st * STAGE_BYTES;
+        for (int k = 0; k < NT; k++) tma_load_2d(stage + k * TILE_BYTES, &P.map[k], box_x, box_y, &full[st]);
+    }
+}
+
+// ----------------------------------------------------------------- poller warp ----
+// Receives the swept variable of the upstream strip's last row into halo_s (indexed by logical
+// column mod HRC) and releases the compute warp group by group through counters[1].
+template <bool BWD>
+__device__ void poller_warp(const TriParams &P, double *halo_s, int sj, int lane, volatile int *dead, unsigned *counters,
+                            const uint4 *ll_ring) {
+    const int ncols = P.nbx * BW;
+    const uint4 *up_row = P.handoff + (size_t)(sj - 1) * ncols;
+    const bool remote = sj == P.sj_base; // the upstream strip belongs to another rank
+    const uint32_t progress_addr = smem_u32(&counters[0]), gate_addr = smem_u32(&counters[1]);
+    Watch watch;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        // a ring slot may be rewritten once the strip's own last row has passed the column it held
+        if (c0 + 32 > HRC) wait_counter(progress_addr, (unsigned)(c0 + 32 - HRC), dead, P.scal);
+        const int c = c0 + lane;
+        const int slot = c % HRC;
+        const uint4 *src = up_row + c;
+        const uint32_t src_s = ll_ring ? smem_u32(ll_ring + slot) : 0;
+        const unsigned tag = ll_ring ? (unsigned)(c / HRC + 1) : P.epoch;
+        bool have = false;
+        unsigned published = 0;
+        while (published < 32) {
+            if (!have) {
+                double v;
+                bool ok;
+                if (ll_ring) {
+                    unsigned a, b, c2, d;
+                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "r"(src_s) : "memory");
+                    v = __hiloint2double((int)c2, (int)a);
+                    ok = b == tag && d == tag;
+                } else {
+                    ok = remote ? ll_load_sys(src, tag, v) : ll_load(src, tag, v);
+                }
+                if (ok) {
+                    halo_s[slot] = v;
+                    have = true;
+                    watch = Watch();
+                } else if (watch.expired(dead)) {
+                    *dead = 1;
+                    P.scal->watchdog = 1;
+                    have = true;
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, have);
+            const unsigned lead = (mask == 0xffffffffu) ? 32u : (unsigned)(__ffs(~mask) - 1);
+            const unsigned groups = lead / HG * HG;
+            if (groups > published) {
+                __threadfence_block(); // halo_s values before the counter
+                if (lane == 0) sts_u32_volatile(gate_addr, (unsigned)c0 + groups);
+                published = groups;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------- storer warp ----
+// Drains the result tile block by block (64 rows x 16 columns, 4 rows per instruction) and folds
+// dotProduct(z, r) (v3:374; masked chapters: non-fluid z is +-0.0 and contributes nothing).  r does
+// not depend on the sweep: its 16 loads per block are issued BEFORE the wait for the block.
+template <bool BWD, bool DOT, bool MASKED>
+__device__ void storer_warp(const TriParams &P, unsigned char *smem, uint64_t *done, uint64_t *empty, int sj, int lane,
+                            volatile int *dead) {
+    const int nbx = P.nbx;
+    const int ty = BWD ? (P.nby - 1 - sj) : sj;
+    const int y0 = ty * SR;
+    const int rs = lane >> 3, cp = (lane & 7) * 2;     // row within a group of 4, first of this lane's two columns
+    const int trow0 = (BWD ? 0 : 1) + rs;              // tile row of memory row y0 + rs
+    double acc = 0.0;
+    for (int b = 0; b < nbx; b++) {
+        const int st = b % NST;
+        const int tx = BWD ? (nbx - 1 - b) : b;
+        const int x = tx * BW + cp;
+        const bool x0 = x < P.W, x1 = x + 1 < P.W;
+        double2 rv[16];
+        if (DOT) {
+            const double *g = P.rdot + x + (size_t)(y0 + rs) * P.pitch;
+#pragma unroll
+            for (int i = 0; i < 16; i++) rv[i] = *reinterpret_cast<const double2 *>(g + (size_t)(4 * i) * P.pitch); // pad rows / columns exist and hold zeros
+        }
+        mbar_wait(&done[st], (unsigned)((b / NST) & 1), dead, P.scal);
+        const unsigned char *stage = smem + (size_t)st * STAGE_BYTES;
+        const double *tile = reinterpret_cast<const double *>(stage) + trow0 * BW + cp;
+        double2 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = *reinterpret_cast<const double2 *>(tile + (4 * i) * BW);
+        if (DOT) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                acc += v[i].x * rv[i].x;
+                acc += v[i].y * rv[i].y;
+            }
+        }
+        double *g = P.dst + x + (size_t)(y0 + rs) * P.pitch;
+        if (!MASKED) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double *d = g + (size_t)(4 * i) * P.pitch;
+                if (y0 + rs + 4 * i < P.H) {
+                    if (x1)
+                        *reinterpret_cast<double2 *>(d) = v[i];
+                    else if (x0)
+                        d[0] = v[i].x;
+                }
+            }
+        } else { // chapters 4+: non-fluid cells keep their old value (v5:751-752); pe is non-zero at fluid cells
+            const double *mt = reinterpret_cast<const double *>(stage + 3 * TILE_BYTES) + trow0 * BW + cp;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const double2 mk = *reinterpret_cast<const double2 *>(mt + (4 * i) * BW);
+                double *d = g + (size_t)(4 * i) * P.pitch;
+                if (y0 + rs + 4 * i < P.H) {
+                    if (x0 && mk.x != 0.0) d[0] = v[i].x;
+                    if (x1 && mk.y != 0.0) d[1] = v[i].y;
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    if (DOT) {
+        const double sum = warp_sum(acc);
+        if (lane == 0) P.partials[sj] = sum;
+    }
+}
+
+// -------------------------------------------------------------- publisher warp ----
+// Forwards the strip's last row to the downstream strip as soon as the compute warp's progress
+// counter says a group of columns is final (see sweep_kernels.cu for the two transports).  It holds
+// each stage until its 16 columns have been sent (second arrival on done[]).
+template <bool BWD>
+__device__ void publisher_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *done, int sj, int lane,
+                               volatile int *dead, unsigned *counters, unsigned rank, uint4 *ll_ring_local) {
+    typedef Geo<BWD> G;
+    const int ncols = P.nbx * BW;
+    const double *last_row = reinterpret_cast<const double *>(smem) + G::last_row() * BW; // tile 0 of stage 0
+    const bool remote = sj + 1 == P.sj_base + P.nloc; // the downstream strip belongs to another rank
+    uint4 *out = (remote ? P.handoff_down : P.handoff) + (size_t)sj * ncols;
+    const uint32_t progress_addr = smem_u32(&counters[0]);
+    const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs && !remote;
+    const uint32_t r_ll = dsmem ? mapa(smem_u32(ll_ring_local), rank + 1) : 0;
+    const uint32_t r_progress = dsmem ? mapa(smem_u32(&counters[0]), rank + 1) : 0;
+    int down_progress = 0; // last value read from the downstream strip's own progress counter
+    int sent = 0;
+    Watch watch;
+    while (sent < ncols) {
+        const int prog = (int)lds_u32_volatile(progress_addr);
+        if (prog > sent) {
+            while (sent < prog) {
+                const int blk = sent / BW;
+                const int blk_end = (blk + 1) * BW;
+                const int upto = prog < blk_end ? prog : blk_end; // stay inside one block
+                const int c = sent + lane;
+                const double *row = last_row + (size_t)(blk % NST) * (STAGE_BYTES / 8);
+                if (dsmem) {
+                    // slot c % HRC is free once the downstream strip's last row has passed column c - HRC
+                    while (upto > HRC && down_progress < upto - HRC) {
+                        down_progress = (int)ld_remote_u32(r_progress);
+                        if (watch.expired(dead)) {
+                            *dead = 1;
+                            P.scal->watchdog = 1;
+                            break;
+                        }
+                    }
+                    if (c < upto) {
+                        const double v = row[G::tcol(c % BW)];
+                        const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v), tag = (unsigned)(c / HRC + 1);
+                        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r_ll + (uint32_t)(c % HRC) * 16u), "r"(lo), "r"(tag),
+                                     "r"(hi), "r"(tag)
+                                     : "memory");
+                    }
+                } else if (c < upto) {
+                    if (remote)
+                        ll_store_sys(out + c, row[G::tcol(c % BW)], P.epoch);
+                    else
+                        ll_store(out + c, row[G::tcol(c % BW)], P.epoch);
+                }
+                sent = upto;
+                if (sent == blk_end) { // all 16 columns of this block are out: the stage may drain
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&done[blk % NST]);
+                }
+            }
+            watch = Watch();
+        } else if (watch.expired(dead)) {
+            *dead = 1;
+            P.scal->watchdog = 1;
+            for (int b = sent / BW; b < P.nbx; b++) // release every stage so that the other warps can finish
+                if (lane == 0) mbar_arrive(&done[b % NST]);
+            return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- kernel ----
+template <bool BWD, bool DOT, bool MASKED>
+__global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[3 * NST]; // full[], done[], empty[]
+    __shared__ int s_ticket;
+    __shared__ int s_dead;
+    __shared__ unsigned s_counters[2]; // [0] columns finished by the last row, [1] hand-off columns received
+    double *halo_s = reinterpret_cast<double *>(smem + (size_t)NST * STAGE_BYTES); // [HRC]
+    uint4 *ll_ring = reinterpret_cast<uint4 *>(halo_s + HRC);                      // [HRC] messages from the cluster neighbour
+    uint64_t *full = bars, *done = bars + NST, *empty = bars + 2 * NST;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = P.cs > 1 ? cluster_ctarank() : 0;
+
+    if (threadIdx.x == 0) {
+        if (rank == 0) s_ticket = (int)(atomicAdd(P.ticket, 1ULL) - P.ticket_base);
+        s_dead = 0;
+        s_counters[0] = 0;
+        s_counters[1] = 0;
+    }
+    if (P.cs > 1)
+        for (int i = threadIdx.x; i < HRC; i += blockDim.x) ll_ring[i] = make_uint4(0u, 0u, 0u, 0u); // tag 0 = empty
+    __syncthreads();
+    int ticket;
+    if (P.cs > 1) {
+        cluster_sync_all(); // every CTA of the cluster is resident, its rings are clear, rank 0's ticket is set
+        ticket = (int)ld_remote_u32(mapa(smem_u32(&s_ticket), 0));
+    } else {
+        ticket = s_ticket;
+    }
+    const int sj = P.sj_base + ticket * P.cs + (int)rank;
+    if (sj >= P.sj_base + P.nloc) return; // padding CTA of the last cluster
+    if (P.gated && P.scal->done) return;  // the solve has converged
+    if (threadIdx.x == 0) {
+        const bool publish = sj + 1 < P.nby;
+        for (int i = 0; i < NST; i++) {
+            mbar_init(&full[i], 1);               // loader's expect_tx arrival (+ TMA bytes)
+            mbar_init(&done[i], publish ? 2 : 1); // compute warp (+ publisher warp)
+            mbar_init(&empty[i], 1);              // storer warp
+        }
+        fence_mbar_init();
+    }
+    if (sj == 0) // the very first strip has no upstream row: its hand-off values read +0.0
+        for (int i = threadIdx.x; i < HRC; i += blockDim.x) halo_s[i] = 0.0;
+    __syncthreads();
+
+    if (warp == 0) {
+        unsigned long long t0 = 0;
+        const long long c0 = clock64();
+        if (P.times && lane == 0) t0 = globaltimer_ns();
+        compute_warp<BWD>(P, smem, halo_s, full, done, sj, lane, &s_dead, s_counters);
+        if (P.times && lane == 0) {
+            P.times[16 * sj] = t0;
+            P.times[16 * sj + 1] = globaltimer_ns();
+            P.times[16 * sj + 15] = (unsigned long long)(clock64() - c0);
+        }
+    } else if (TRI_EXP & 2) {
+        // (experiment: no helper warps)
+    } else if (warp == 1) {
+        loader_warp<BWD>(P, smem, full, empty, sj, lane, &s_dead);
+    } else if (warp == 2) {
+        storer_warp<BWD, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
+    } else if (warp == 3) {
+        if (sj + 1 < P.nby) publisher_warp<BWD>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank, ll_ring);
+    } else if (warp == 5 && sj > 0) {
+        // first strip of a cluster (and of a rank): its upstream strip talks through L2 / NVLink
+        poller_warp<BWD>(P, halo_s, sj, lane, &s_dead, s_counters, (rank == 0 || sj == P.sj_base) ? nullptr : ll_ring);
+    }
+}
+
+} // namespace tri
+
+// ------------------------------------------------------------------- host side ----
+static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
+
+template <bool BWD, bool DOT>
+static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdot, bool gated) {
+    using namespace tri;
+    TriParams P;
+    memset(&P, 0, sizeof P);
+    const Arr *ops[NT] = {&rhs, &c->cx, &c->cy, &precon_operand(c)};
+    for (int k = 0; k < NT; k++) {
+        int rc = sweep_get_map(c, *ops[k], BW, TROWS, &P.map[k]);
+        if (rc != IFL_OK) return rc;
+    }
+    P.dst = dst.p;
+    P.rdot = rdot ? rdot->p : nullptr;
+    P.W = c->W;
+    P.H = c->H;
+    P.pitch = c->r.pitch;
+    P.nbx = c->r.pitch / BW;
+    P.nby = (c->H + SR - 1) / SR;
+    P.handoff = reinterpret_cast<uint4 *>(c->handoff);
+    c->epoch++;
+    P.epoch = (unsigned)(c->epoch & 0xffffffffu);
+    if (P.epoch == 0) { // 0 is the value of never-written hand-off slots
+        c->epoch++;
+        P.epoch = 1;
+    }
+    P.cs = c->sweep_cluster;
+    {   // this rank's strips, in sweep order (slabs are whole 64-row strips, dist.cu)
+        const int s0 = c->ry0 / SR, s1 = (c->ry1 + SR - 1) / SR;
+        P.nloc = s1 - s0;
+        P.sj_base = BWD ? P.nby - s1 : s0;
+        P.handoff_down = reinterpret_cast<uint4 *>(c->handoff_down[BWD ? 1 : 0]);
+    }
+    const int n_clusters = (P.nloc + P.cs - 1) / P.cs;
+    P.ticket = c->ticket;
+    P.ticket_base = c->sweep_tickets;
+    c->sweep_tickets += (unsigned long long)n_clusters;
+    c->sweep_launches++;
+    P.scal = c->scal;
+    P.gated = gated ? 1 : 0;
+    P.head_delay = c->sweep_head_delay;
+    P.times = c->sweep_times;
+    if (DOT) {
+        P.partials = partials_next(c);
+        c->n_partials = P.nby;
+    }
+    const size_t smem = (size_t)NST * STAGE_BYTES + (size_t)HRC * sizeof(double) + (size_t)HRC * sizeof(uint4);
+    const bool masked = c->version >= 4;
+    static bool attr_set[IFL_MAX_DEVICES][2][2][2]; // function attributes are per device
+    auto kern = masked ? k_tri<BWD, DOT, true> : k_tri<BWD, DOT, false>;
+    if (!attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked]) {
+        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked] = true;
+    }
+    ProfScope ps_(c, BWD ? IFL_K_PRECON_BWD : IFL_K_PRECON_FWD);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = P.cs > 1 ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, P);
+    if (le != cudaSuccess) {
+        set_error("triangular solve launch (cluster %d) -> %s", P.cs, cudaGetErrorString(le));
+        return IFL_E_CUDA;
+    }
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
+int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
+    return launch_tri<false, false>(c, a, dst, nullptr, gated);
+}
+
+int launch_tri_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
+    if (with_dot) return launch_tri<true, true>(c, dst, dst, &r_for_dot, gated);
+    return launch_tri<true, false>(c, dst, dst, nullptr, gated);
+}
+
+} // namespace ifl

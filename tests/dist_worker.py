@@ -50,7 +50,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     multi = make_solver(chapter, w, h, device=rank, rank=rank, world=world, rendezvous=rdv)
     r0, r1 = multi.rows()
-    assert r0 % 32 == 0 and r0 < r1 <= h, (r0, r1)
+    assert r0 % 64 == 0 and r0 < r1 <= h, (r0, r1)
     rng = np.random.default_rng(7)
     rvec = rng.uniform(-1, 1, w * h)
     gran = {}

@@ -27,13 +27,13 @@ def test_plan_tiles_the_grid_in_whole_strips():
     L = ifl.load_library()
     for h in (32, 64, 100, 128, 136, 1000, 4096, 16384):
         for world in range(1, 9):
-            if (h + 31) // 32 < world:
+            if (h + 63) // 64 < world:
                 assert plan(L, h, world, 0)[0] != 0
                 continue
             prev = 0
             for r in range(world):
                 rc, a, b = plan(L, h, world, r)
-                assert rc == 0 and a == prev and a % 32 == 0 and b > a
+                assert rc == 0 and a == prev and a % 64 == 0 and b > a
                 prev = b
             assert prev == h
     rc, a, b = plan(L, 4096, 8, 3)
@@ -67,8 +67,8 @@ def test_two_gloo_ranks_rendezvous_and_plan():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # [plan rc, row0, row1, selftest rc] per rank: 200 rows = 7 strips -> 3 + 4
-    assert res == [[0, 0, 96, 0], [0, 96, 200, 0]], res
+    # [plan rc, row0, row1, selftest rc] per rank: 200 rows = 4 strips of 64 rows -> 2 + 2
+    assert res == [[0, 0, 128, 0], [0, 128, 200, 0]], res
 
 
 def test_create_dist_without_gpu_fails_loudly():
