@@ -450,28 +450,29 @@ class FluidSolver:
             u, v = rest
             self._chk(self.L.ifl_add_inflow(self.ctx, x, y, w, h, d, u, v))
 
-    def update(self, timestep):
-        if self.version >= 4:
-            self.syncBodies()
+    def _record_update(self, infos):
+        """infos: (SolveInfo * 2); chapters 6+ fill [0] = heat solve, [1] = pressure solve."""
         if self.version >= 6:
-            infos = (SolveInfo * 2)()
-            self._chk(self.L.ifl_update(self.ctx, timestep, self.density, infos))
             self._record(infos[0])
             self.last_heat = self.last
             self._record(infos[1])
-            return self.last
-        info = SolveInfo()
-        self._chk(self.L.ifl_update(self.ctx, timestep, self.density, ctypes.byref(info)))
-        self._record(info)
+        else:
+            self._record(infos[0])
         return self.last
+
+    def update(self, timestep):
+        if self.version >= 4:
+            self.syncBodies()
+        infos = (SolveInfo * 2)()
+        self._chk(self.L.ifl_update(self.ctx, timestep, self.density, infos))
+        return self._record_update(infos)
 
     def update_host(self, timestep, d, u, v):
         """update() on HOST arrays (in/out, reference layout): H2D + step + D2H."""
-        info = SolveInfo()
+        infos = (SolveInfo * 2)()  # chapters 6+ report two solves (heat, pressure)
         self._chk(self.L.ifl_update_host(self.ctx, timestep, self.density, d.ctypes.data, u.ctypes.data,
-                                         v.ctypes.data, ctypes.byref(info)))
-        self._record(info)
-        return self.last
+                                         v.ctypes.data, infos))
+        return self._record_update(infos)
 
     def slab_elems(self, name):
         return self.L.ifl_slab_elems(self.ctx, BUF[name])
@@ -484,11 +485,10 @@ class FluidSolver:
 
     def update_host_slab(self, timestep, d, u, v):
         """update() on HOST arrays holding this rank's slab rows only (in/out)."""
-        info = SolveInfo()
+        infos = (SolveInfo * 2)()
         self._chk(self.L.ifl_update_host_slab(self.ctx, timestep, self.density, d.ctypes.data, u.ctypes.data,
-                                              v.ctypes.data, ctypes.byref(info)))
-        self._record(info)
-        return self.last
+                                              v.ctypes.data, infos))
+        return self._record_update(infos)
 
     def toImage(self):
         d = self.get("d.src")

@@ -102,6 +102,38 @@ __global__ void k_add_inflow(Arr src, int ix_lo, int ix_hi, int iy_lo, int iy_hi
     if (fabs(src.p[i]) < fabs(vi)) src.p[i] = vi;
 }
 
+// The same stamp on a w < h grid whose x range runs past the row (the `_h` clamp, quirk 2): the
+// reference's dense index x + y*_w then lands in the following rows, cell (x mod w, y + x div w).
+// One thread per TARGET cell applies its sources in the reference's raster order (ascending y), so the
+// result is exact and race-free; targets past the last row (the reference writes out of bounds there)
+// are dropped.
+__global__ void k_add_inflow_wrap(Arr src, int ix_lo, int ix_hi, int iy_lo, int iy_hi, double hx, double x0, double y0,
+                                  double x1, double y1, double v, int smooth) {
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ty = src.ry0 + blockIdx.y;
+    if (tx >= src.w || ty >= src.ry1) return;
+    const size_t i = tx + (size_t)ty * src.pitch;
+    double cur = src.p[i];
+    bool touched = false;
+    for (int j = (ix_hi - 1 - tx) / src.w; j >= 0; j--) { // source (tx + j*w, ty - j): ascending y
+        const int x = tx + j * src.w, y = ty - j;
+        if (x < ix_lo || x >= ix_hi || y < iy_lo || y >= iy_hi) continue;
+        double vi = v;
+        if (smooth) {
+            const double lx = (2.0 * (x + 0.5) * hx - (x0 + x1)) / (x1 - x0);
+            const double ly = (2.0 * (y + 0.5) * hx - (y0 + y1)) / (y1 - y0);
+            const double l = sqrt(lx * lx + ly * ly);
+            const double xx = std_min(fabs(l), 1.0);
+            vi = (1.0 - xx * xx * (3.0 - 2.0 * xx)) * v;
+        }
+        if (fabs(cur) < fabs(vi)) {
+            cur = vi;
+            touched = true;
+        }
+    }
+    if (touched) src.p[i] = cur;
+}
+
 // ---------------------------------------------------------- chapters 4+ variants ----
 __device__ __forceinline__ double bvx(const BodyDev &b, double y) { return (b.posY - y) * b.velTheta + b.velX; } // v4:125
 __device__ __forceinline__ double bvy(const BodyDev &b, double x) { return (x - b.posX) * b.velTheta + b.velY; } // v4:129
@@ -443,13 +475,18 @@ int launch_add_inflow(ifl_ctx *c, int field, double x0, double y0, double x1, do
     const int ix1 = (int)(x1 / c->hx - f.ox);
     const int iy1 = (int)(y1 / c->hx - f.oy);
     const int xlo = imax(ix0, 0), xhi = imin(ix1, f.h); // sic: _h (v2:195)
+    if (xhi > f.w) { // only on w < h grids: the stamp runs past the row and wraps into the following rows
+        const int rlo = imax(iy0, 0), rhi = imin(iy1, f.h);
+        if (xhi <= xlo || rhi <= rlo || f.src.ry1 <= f.src.ry0) return IFL_OK;
+        ProfScope ps_(c, IFL_K_ASSEMBLY);
+        k_add_inflow_wrap<<<dim3((f.w + 127) / 128, f.src.ry1 - f.src.ry0), 128, 0, c->stream>>>(
+            f.src, xlo, xhi, rlo, rhi, c->hx, x0, y0, x1, y1, v, c->version >= 2 ? 1 : 0);
+        IFL_LAUNCHED(c);
+        return IFL_OK;
+    }
     // rows: the reference's clamp, then this rank's slab
     const int ylo = imax(imax(iy0, 0), f.src.ry0), yhi = imin(imin(iy1, f.h), f.src.ry1);
     if (xhi <= xlo || yhi <= ylo) return IFL_OK;
-    if (xhi > f.src.pitch) { // only reachable on w < h grids, where the reference itself reads out of row
-        set_error("addInflow: x range [%d,%d) exceeds the row pitch on a w<h grid", xlo, xhi);
-        return IFL_E_ARG;
-    }
     dim3 grid((xhi - xlo + 127) / 128, yhi - ylo);
     ProfScope ps_(c, IFL_K_ASSEMBLY);
     k_add_inflow<<<grid, 128, 0, c->stream>>>(f.src, xlo, xhi, ylo, yhi, c->hx, x0, y0, x1, y1, v,

@@ -29,8 +29,20 @@
 //     reads column (k - t) mod 16: the 16 lanes of a half-warp hit 16 different 8-byte bank slots.
 //   * warps: 0 compute, 1 TMA loader, 2 storer (drains z, folds z.r reading r straight from global
 //     memory -- it does not depend on the sweep, so its loads are issued before the wait), 3 publisher,
-//     5 poller (strip-to-strip hand-off, same protocol as sweep_kernels.cu: LL messages through the
-//     downstream CTA's shared memory inside a thread-block cluster, through L2 / NVLink otherwise).
+//     5 gatekeeper (strip-to-strip hand-off + TMA arrival -> one "gate" counter for the compute warp).
+//   * NOBODY POLLS shared memory while the compute warp runs.  Measured (profiles/r02_tri_experiments.txt):
+//     with a publisher spinning on the progress counter and a poller spinning on the message ring the
+//     compute warp needs 129 cycles per step, without any helper warp 98 -- their shared-memory polls
+//     queue up in front of the recurrence's own LDS / SHFL.  So every helper sleeps on an mbarrier:
+//       - the compute warp rings a "bell" (mbarrier.arrive, ring of 16) every 8 columns its last row
+//         completes; the publisher sleeps on it, then forwards those 8 values;
+//       - inside a thread-block cluster the values travel as st.async (8 bytes + complete_tx) straight
+//         into the downstream CTA's hand-off ring and count on one of ITS 64 group mbarriers, on which
+//         its gatekeeper sleeps; between clusters and between GPUs they travel as NCCL-LL style
+//         {lo, epoch, hi, epoch} messages through L2 / NVLink, which the gatekeeper polls in GLOBAL
+//         memory (with a back-off);
+//       - the gatekeeper also waits for the TMA ring (`full` barriers), so the compute warp never
+//         executes an mbarrier wait: it reads one shared counter every 8 steps, four steps ahead of use.
 #include "ifl_internal.cuh"
 #include "sweep_common.cuh"
 
@@ -40,9 +52,11 @@
 #include <string.h>
 
 // Timing experiments (profiles/tri_experiments.sh builds one library per value; never set in the
-// product build): bit 0 no fence.proxy.async in the compute warp, bit 1 no ring barriers at all (the
-// compute warp runs over whatever is in shared memory: garbage results, pure step time), bit 2 no
-// progress stores, bit 3 no lane-0 hand-off select.
+// product build; results are garbage, only strip 0's step time is of interest): bit 1 (2) no helper
+// warps, gate preset to "everything is there"; bit 2 (4) no progress store / bell; bit 3 (8) no lane-0
+// hand-off select; bit 4 (16) no gate checks; bit 5 (32) no done[] arrival; bit 7 (128) the storer does
+// not drain (waits and releases only); bit 8 (256) the loader arrives on `full` without loading;
+// bit 9 (512) no hand-off at all: no publisher, every strip runs as if it were the first.
 #ifndef TRI_EXP
 #define TRI_EXP 0
 #endif
@@ -60,6 +74,8 @@ constexpr int STAGE_BYTES = NT * TILE_BYTES;  // 33280
 constexpr int NST = 6;                        // ring depth
 constexpr int HG = 8;                         // hand-off granularity (columns)
 constexpr int HRC = 512;                      // hand-off ring (columns): deep enough that back-pressure never binds
+constexpr int NHB = HRC / HG;                 // hand-off group barriers (one per ring group)
+constexpr int NBELL = 16;                     // bell ring (the publisher is never NST blocks = 12 groups behind)
 
 struct TriParams {
     CUtensorMap map[NT]; // must stay first (64-byte aligned)
@@ -133,23 +149,22 @@ __device__ __forceinline__ uint32_t pos(const LaneBases &lb, int j, int r) {
 // their stores predicated off; what they compute is never consumed (lane t-1 is inside at step k-1
 // exactly when lane t is inside at step k).
 template <bool BWD, int EDGE>
-__device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next, uint64_t *full_next,
-                                           unsigned parity_next, bool wait_next, int m, int lane, int r, Carry &cr, Ops &ops,
-                                           uint32_t progress_addr, uint32_t gate_addr, bool has_up, int ncols,
-                                           volatile int *dead, SolveScalars *scal) {
+__device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next, uint32_t bell6, uint32_t bell14,
+                                           int m, int lane, int r, Carry &cr, Ops &ops, uint32_t progress_addr,
+                                           uint32_t gate_addr, int ncols, volatile int *dead, SolveScalars *scal) {
     typedef Geo<BWD> G;
     uint32_t p = pos<BWD>(lb, 0, r);
     unsigned gate_seen = 0;
 #pragma unroll
     for (int kk = 0; kk < BW; kk++) {
-        if (kk == BW - 1 && wait_next && !(TRI_EXP & 2)) mbar_wait(full_next, parity_next, dead, scal); // lanes 0/16 are about to touch the next block
-        // hand-off gate: read four steps early, tested when lane 0 is about to need the next group
-        if (((kk + 5) % HG) == 0 && has_up && EDGE != 2) gate_seen = lds_u32_volatile(gate_addr);
-        if (((kk + 1) % HG) == 0 && has_up && EDGE != 2) {
+        // gate (hand-off values received AND operand blocks loaded, in columns): read four steps early,
+        // tested when lane 0 is about to fetch the first column of the next group
+        if (((kk + 5) % HG) == 0 && EDGE != 2 && !(TRI_EXP & 16)) gate_seen = lds_u32_volatile(gate_addr);
+        if (((kk + 1) % HG) == 0 && EDGE != 2 && !(TRI_EXP & 16)) {
             const unsigned need = (unsigned)imin(BW * m + kk + 1 + HG, ncols);
             if (gate_seen < need) wait_counter<false>(gate_addr, need, dead, scal);
         }
-        // ---- critical path first: the upstream lane's B of the previous step
+        // ---- critical path first: the upstream lane's B of the previous step (lane 0: the hand-off value)
         double up = __shfl_up_sync(0xffffffffu, cr.zB, 1);
         // ---- operands of step kk+1, in the shadow of the shuffle
         Ops nxt;
@@ -168,6 +183,9 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
                 cr.cB = sel_f64(first, 0.0, cr.cB);
             }
         }
+        // (lane 0 takes the hand-off value.  Tried: a rotating shuffle with lane 31 carrying the hand-off value
+        // in the shuffled register -- ptxas turns the predicated duplicate multiply into four FSELs on the
+        // chain, slower than this one select pair.)
         if (!(TRI_EXP & 8)) up = sel_f64(lane == 0, ops.halo, up);
         double zA, zB;
         if (!BWD) {
@@ -191,20 +209,25 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         sts_f64_p<EDGE == 0>(p + (uint32_t)G::ROW_B, zB, active);
         cr.zA = zA;
         cr.zB = zB;
-        // the strip's last row (lane 31, cell B) has just completed another group of HG columns
-        if (((kk + 2) % HG) == 0 && !(TRI_EXP & 4)) sts_u32_volatile(progress_addr, (unsigned)imin(imax(BW * m + kk - 30, 0), ncols));
+        // the strip's last row (lane 31, cell B) has just completed another group of HG columns: publish
+        // the count and ring the publisher's bell (lane 31 wrote those values itself: its arrive releases them)
+        if (((kk + 2) % HG) == 0 && EDGE != 1 && !(TRI_EXP & 4)) {
+            sts_u32_volatile(progress_addr, (unsigned)imin(BW * m + kk - 30, ncols));
+            if (lane == 31) mbar_arrive_addr(kk < HG ? bell6 : bell14);
+        }
         ops = nxt;
         p = pn;
     }
 }
 
 template <bool BWD>
-__device__ void compute_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *full, uint64_t *done, int sj,
+__device__ void compute_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *done, uint64_t *bell, int sj,
                              int lane, volatile int *dead, unsigned *counters) {
     typedef Geo<BWD> G;
     Carry cr;
     cr.zA = cr.zB = cr.cA = cr.cB = 0.0;
-    const bool has_up = sj > 0 && !(TRI_EXP & 2);
+    const bool has_up = sj > 0;
+    (void)has_up;
     const uint32_t progress_addr = smem_u32(&counters[0]), gate_addr = smem_u32(&counters[1]);
     const int nbx = P.nbx, ncols = P.nbx * BW;
     const int q = lane >> 4, r = lane & 15;
@@ -228,12 +251,8 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
     Ops ops;
     // everything that does not depend on the upstream strip happens BEFORE the wait for its first
     // hand-off group: that wait sits on the critical path of the whole sweep
-    if (!(TRI_EXP & 2)) mbar_wait(&full[0], 0, dead, P.scal);
+    wait_counter<false>(gate_addr, (unsigned)imin(HG, ncols), dead, P.scal); // block 0 loaded, first hand-off group here
     fetch<BWD>(ops, pos<BWD>(bases(0), 0, r), halo0); // step 0: lane 0 at column 0, the others idle on valid memory
-    if (has_up) {
-        wait_counter<false>(gate_addr, (unsigned)imin(HG, ncols), dead, P.scal);
-        ops.halo = lds_f64(halo0);
-    }
     const int nm = nbx + 2; // macro-steps: lane 31 finishes column ncols-1 at step ncols + 30
     for (int m = 0; m < nm; m++) {
         if (!has_up && P.head_delay > 0) { // pace-setter, see sweep_init
@@ -243,21 +262,16 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
         const LaneBases lb = bases(m);
         const uint32_t h_cur = halo0 + (uint32_t)(((BW * m) % HRC) * 8);
         const uint32_t h_next = halo0 + (uint32_t)(((BW * (m + 1)) % HRC) * 8);
-        const bool wait_next = m + 1 < nbx; // block m+1 exists: lane 0 steps into it at the look-ahead
-        uint64_t *full_next = &full[(m + 1) % NST];
-        const unsigned parity_next = (unsigned)(((m + 1) / NST) & 1);
+        // groups completed by the last row at kk == 6 / 14 of this macro-step: 2m-4, 2m-3 (m >= 2)
+        const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 4) % NBELL]), bell14 = smem_u32(&bell[(2 * m + NBELL - 3) % NBELL]);
         if (m < 2)
-            macro_step<BWD, 1>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
-                               has_up, ncols, dead, P.scal);
+            macro_step<BWD, 1>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         else if (m >= nbx)
-            macro_step<BWD, 2>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
-                               has_up, ncols, dead, P.scal);
+            macro_step<BWD, 2>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         else
-            macro_step<BWD, 0>(lb, h_cur, h_next, full_next, parity_next, wait_next, m, lane, r, cr, ops, progress_addr, gate_addr,
-                               has_up, ncols, dead, P.scal);
-        if (m >= 2 && !(TRI_EXP & 2)) { // lane 31 has left block m-2: hand it to the storer (and, through it, the loader)
-            if (!(TRI_EXP & 1)) fence_proxy_async();
-            __syncwarp();
+            macro_step<BWD, 0>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
+        if (m >= 2 && !(TRI_EXP & 32)) { // lane 31 has left block m-2: hand it to the storer (and, through it, the loader;
+            __syncwarp();               // the storer issues the proxy fence before the TMA may overwrite the stage)
             if (lane == 0) mbar_arrive(&done[(m - 2) % NST]);
         }
     }
@@ -274,6 +288,10 @@ __device__ void loader_warp(const TriParams &P, unsigned char *smem, uint64_t *f
     for (int b = 0; b < nbx; b++) {
         const int st = b % NST;
         if (b >= NST) mbar_wait(&empty[st], (unsigned)(((b / NST) - 1) & 1), dead, P.scal);
+        if (TRI_EXP & 256) {
+            mbar_arrive(&full[st]);
+            continue;
+        }
         mbar_arrive_expect_tx(&full[st], (unsigned)STAGE_BYTES);
         const int box_x = (BWD ? (nbx - 1 - b) : b) * BW;
         unsigned char *stage = smem + (size_t)st * STAGE_BYTES;
@@ -281,57 +299,70 @@ __device__ void loader_warp(const TriParams &P, unsigned char *smem, uint64_t *f
     }
 }
 
-// ----------------------------------------------------------------- poller warp ----
-// Receives the swept variable of the upstream strip's last row into halo_s (indexed by logical
-// column mod HRC) and releases the compute warp group by group through counters[1].
+// ------------------------------------------------------------- gatekeeper warp ----
+// Releases the compute warp group by group (HG columns) through counters[1]: a group is released when
+// the upstream strip's last-row values for it are in halo_s (indexed by logical column mod HRC) AND the
+// operand block it lies in has landed.  `hb` != null: the upstream strip runs in the same cluster and
+// sends st.async + complete_tx on hb[group % NHB] (armed here with expect_tx); otherwise the values
+// arrive as LL messages in global memory (L2, or NVLink for the first strip of a rank).
 template <bool BWD>
-__device__ void poller_warp(const TriParams &P, double *halo_s, int sj, int lane, volatile int *dead, unsigned *counters,
-                            const uint4 *ll_ring) {
+__device__ void gatekeeper_warp(const TriParams &P, double *halo_s, uint64_t *full, uint64_t *hb, int sj, int lane,
+                                volatile int *dead, unsigned *counters) {
     const int ncols = P.nbx * BW;
-    const uint4 *up_row = P.handoff + (size_t)(sj - 1) * ncols;
+    const bool has_up = sj > 0 && !(TRI_EXP & 512);
+    const uint4 *up_row = P.handoff + (size_t)(has_up ? sj - 1 : 0) * ncols;
     const bool remote = sj == P.sj_base; // the upstream strip belongs to another rank
     const uint32_t progress_addr = smem_u32(&counters[0]), gate_addr = smem_u32(&counters[1]);
     Watch watch;
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
+    mbar_wait(&full[0], 0, dead, P.scal); // operand block 0
+    if (has_up && !hb) {
+        // LL messages in global memory: one L2 (NVLink) round trip serves 32 columns -- a poll per group of 8
+        // would not keep up with the producer (a round trip outlasts 8 steps) -- and groups are released as
+        // their messages turn up
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            if (c0 + 32 > HRC) wait_counter(progress_addr, (unsigned)(c0 + 32 - HRC), dead, P.scal);
+            for (int b = c0 / BW; b <= (c0 + 31) / BW && b * BW < ncols; b++) // both operand blocks of this chunk
+                if (b > 0) mbar_wait(&full[b % NST], (unsigned)((b / NST) & 1), dead, P.scal);
+            const int c = c0 + lane;
+            bool have = false;
+            unsigned published = 0;
+            while (published < 32) {
+                if (!have) {
+                    double v;
+                    if (remote ? ll_load_sys(up_row + c, P.epoch, v) : ll_load(up_row + c, P.epoch, v)) {
+                        halo_s[c % HRC] = v;
+                        have = true;
+                        watch = Watch();
+                    } else if (watch.expired(dead)) {
+                        *dead = 1;
+                        P.scal->watchdog = 1;
+                        have = true;
+                    }
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, have);
+                const unsigned lead = (mask == 0xffffffffu) ? 32u : (unsigned)(__ffs(~mask) - 1);
+                const unsigned groups = lead / HG * HG;
+                if (groups > published) {
+                    __threadfence_block(); // halo_s values before the counter
+                    if (lane == 0) sts_u32_volatile(gate_addr, (unsigned)c0 + groups);
+                    published = groups;
+                }
+            }
+        }
+        return;
+    }
+    for (int c0 = 0; c0 < ncols; c0 += HG) {
+        const int g = c0 / HG;
         // a ring slot may be rewritten once the strip's own last row has passed the column it held
-        if (c0 + 32 > HRC) wait_counter(progress_addr, (unsigned)(c0 + 32 - HRC), dead, P.scal);
-        const int c = c0 + lane;
-        const int slot = c % HRC;
-        const uint4 *src = up_row + c;
-        const uint32_t src_s = ll_ring ? smem_u32(ll_ring + slot) : 0;
-        const unsigned tag = ll_ring ? (unsigned)(c / HRC + 1) : P.epoch;
-        bool have = false;
-        unsigned published = 0;
-        while (published < 32) {
-            if (!have) {
-                double v;
-                bool ok;
-                if (ll_ring) {
-                    unsigned a, b, c2, d;
-                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(d) : "r"(src_s) : "memory");
-                    v = __hiloint2double((int)c2, (int)a);
-                    ok = b == tag && d == tag;
-                } else {
-                    ok = remote ? ll_load_sys(src, tag, v) : ll_load(src, tag, v);
-                }
-                if (ok) {
-                    halo_s[slot] = v;
-                    have = true;
-                    watch = Watch();
-                } else if (watch.expired(dead)) {
-                    *dead = 1;
-                    P.scal->watchdog = 1;
-                    have = true;
-                }
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, have);
-            const unsigned lead = (mask == 0xffffffffu) ? 32u : (unsigned)(__ffs(~mask) - 1);
-            const unsigned groups = lead / HG * HG;
-            if (groups > published) {
-                __threadfence_block(); // halo_s values before the counter
-                if (lane == 0) sts_u32_volatile(gate_addr, (unsigned)c0 + groups);
-                published = groups;
-            }
+        if (has_up && c0 + HG > HRC) wait_counter(progress_addr, (unsigned)(c0 + HG - HRC), dead, P.scal);
+        if (has_up) mbar_wait(&hb[g % NHB], (unsigned)((g / NHB) & 1), dead, P.scal);
+        if (lane == 0) sts_u32_volatile(gate_addr, (unsigned)(c0 + HG));
+        // ---- off the critical path: arm the group barrier for its next use (NHB groups from now) and make sure
+        // the operand block of the NEXT group has landed (the TMA ring runs far ahead: this returns at once)
+        if (has_up && lane == 0) mbar_arrive_expect_tx(&hb[g % NHB], HG * 8);
+        if ((c0 + HG) % BW == 0 && c0 + HG < ncols) {
+            const int b = (c0 + HG) / BW;
+            mbar_wait(&full[b % NST], (unsigned)((b / NST) & 1), dead, P.scal);
         }
     }
 }
@@ -340,27 +371,48 @@ __device__ void poller_warp(const TriParams &P, double *halo_s, int sj, int lane
 // Drains the result tile block by block (64 rows x 16 columns, 4 rows per instruction) and folds
 // dotProduct(z, r) (v3:374; masked chapters: non-fluid z is +-0.0 and contributes nothing).  r does
 // not depend on the sweep: its 16 loads per block are issued BEFORE the wait for the block.
+// Two storer warps share the work (even / odd blocks): one block lasts ~1 us of sweep, and a storer that
+// also folds the dot product needs ~1.4 us per block (r from L2, 64 FP64 ops, 16 stores, proxy fence),
+// which throttled the whole ring (measured: 168 instead of 121 cycles per step).
 template <bool BWD, bool DOT, bool MASKED>
 __device__ void storer_warp(const TriParams &P, unsigned char *smem, uint64_t *done, uint64_t *empty, int sj, int lane,
-                            volatile int *dead) {
+                            volatile int *dead, int which) {
     const int nbx = P.nbx;
     const int ty = BWD ? (P.nby - 1 - sj) : sj;
     const int y0 = ty * SR;
     const int rs = lane >> 3, cp = (lane & 7) * 2;     // row within a group of 4, first of this lane's two columns
     const int trow0 = (BWD ? 0 : 1) + rs;              // tile row of memory row y0 + rs
-    double acc = 0.0;
-    for (int b = 0; b < nbx; b++) {
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0; // four fixed interleaved partial sums (shorter dependency chain)
+    constexpr int PF = 4; // r is pulled into L2 this many of this warp's blocks ahead of its use
+    if (DOT)
+        for (int b = which; b < 2 * PF && b < nbx; b += 2) {
+            const int tx = BWD ? (nbx - 1 - b) : b;
+            const double *g = P.rdot + tx * BW + (size_t)(y0 + 2 * lane) * P.pitch;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g + P.pitch));
+        }
+    for (int b = which; b < nbx; b += 2) {
         const int st = b % NST;
         const int tx = BWD ? (nbx - 1 - b) : b;
         const int x = tx * BW + cp;
         const bool x0 = x < P.W, x1 = x + 1 < P.W;
         double2 rv[16];
         if (DOT) {
+            if (b + 2 * PF < nbx) { // one 128-byte line per row of block b + 2 PF: lane t takes rows 2t, 2t + 1
+                const int txp = BWD ? (nbx - 1 - (b + 2 * PF)) : (b + 2 * PF);
+                const double *gp = P.rdot + txp * BW + (size_t)(y0 + 2 * lane) * P.pitch;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + P.pitch));
+            }
             const double *g = P.rdot + x + (size_t)(y0 + rs) * P.pitch;
 #pragma unroll
             for (int i = 0; i < 16; i++) rv[i] = *reinterpret_cast<const double2 *>(g + (size_t)(4 * i) * P.pitch); // pad rows / columns exist and hold zeros
         }
         mbar_wait(&done[st], (unsigned)((b / NST) & 1), dead, P.scal);
+        if (TRI_EXP & 128) {
+            if (lane == 0) mbar_arrive(&empty[st]);
+            continue;
+        }
         const unsigned char *stage = smem + (size_t)st * STAGE_BYTES;
         const double *tile = reinterpret_cast<const double *>(stage) + trow0 * BW + cp;
         double2 v[16];
@@ -368,9 +420,11 @@ __device__ void storer_warp(const TriParams &P, unsigned char *smem, uint64_t *d
         for (int i = 0; i < 16; i++) v[i] = *reinterpret_cast<const double2 *>(tile + (4 * i) * BW);
         if (DOT) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                acc += v[i].x * rv[i].x;
-                acc += v[i].y * rv[i].y;
+            for (int i = 0; i < 16; i += 2) {
+                acc0 += v[i].x * rv[i].x;
+                acc1 += v[i].y * rv[i].y;
+                acc2 += v[i + 1].x * rv[i + 1].x;
+                acc3 += v[i + 1].y * rv[i + 1].y;
             }
         }
         double *g = P.dst + x + (size_t)(y0 + rs) * P.pitch;
@@ -402,89 +456,78 @@ __device__ void storer_warp(const TriParams &P, unsigned char *smem, uint64_t *d
         if (lane == 0) mbar_arrive(&empty[st]);
     }
     if (DOT) {
-        const double sum = warp_sum(acc);
-        if (lane == 0) P.partials[sj] = sum;
+        const double sum = warp_sum((acc0 + acc1) + (acc2 + acc3));
+        if (lane == 0) P.partials[2 * sj + which] = sum;
     }
 }
 
 // -------------------------------------------------------------- publisher warp ----
-// Forwards the strip's last row to the downstream strip as soon as the compute warp's progress
-// counter says a group of columns is final (see sweep_kernels.cu for the two transports).  It holds
-// each stage until its 16 columns have been sent (second arrival on done[]).
+// Forwards the strip's last row to the downstream strip, HG columns at a time: it sleeps on the bell
+// the compute warp rings for every completed group, reads the 8 values from the result tile and sends
+// them (st.async into the downstream CTA's ring inside a cluster, LL messages through L2 / NVLink
+// otherwise).  It holds each stage until its 16 columns have been sent (second arrival on done[]).
 template <bool BWD>
-__device__ void publisher_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *done, int sj, int lane,
-                               volatile int *dead, unsigned *counters, unsigned rank, uint4 *ll_ring_local) {
+__device__ void publisher_warp(const TriParams &P, unsigned char *smem, double *halo_s, uint64_t *done, uint64_t *bell,
+                               uint64_t *hb, int sj, int lane, volatile int *dead, unsigned *counters, unsigned rank) {
     typedef Geo<BWD> G;
     const int ncols = P.nbx * BW;
     const double *last_row = reinterpret_cast<const double *>(smem) + G::last_row() * BW; // tile 0 of stage 0
     const bool remote = sj + 1 == P.sj_base + P.nloc; // the downstream strip belongs to another rank
     uint4 *out = (remote ? P.handoff_down : P.handoff) + (size_t)sj * ncols;
-    const uint32_t progress_addr = smem_u32(&counters[0]);
     const bool dsmem = P.cs > 1 && rank + 1 < (unsigned)P.cs && !remote;
-    const uint32_t r_ll = dsmem ? mapa(smem_u32(ll_ring_local), rank + 1) : 0;
+    const uint32_t r_halo = dsmem ? mapa(smem_u32(halo_s), rank + 1) : 0;
+    const uint32_t r_hb = dsmem ? mapa(smem_u32(hb), rank + 1) : 0;
     const uint32_t r_progress = dsmem ? mapa(smem_u32(&counters[0]), rank + 1) : 0;
     int down_progress = 0; // last value read from the downstream strip's own progress counter
-    int sent = 0;
     Watch watch;
-    while (sent < ncols) {
-        const int prog = (int)lds_u32_volatile(progress_addr);
-        if (prog > sent) {
-            while (sent < prog) {
-                const int blk = sent / BW;
-                const int blk_end = (blk + 1) * BW;
-                const int upto = prog < blk_end ? prog : blk_end; // stay inside one block
-                const int c = sent + lane;
-                const double *row = last_row + (size_t)(blk % NST) * (STAGE_BYTES / 8);
-                if (dsmem) {
-                    // slot c % HRC is free once the downstream strip's last row has passed column c - HRC
-                    while (upto > HRC && down_progress < upto - HRC) {
-                        down_progress = (int)ld_remote_u32(r_progress);
-                        if (watch.expired(dead)) {
-                            *dead = 1;
-                            P.scal->watchdog = 1;
-                            break;
-                        }
-                    }
-                    if (c < upto) {
-                        const double v = row[G::tcol(c % BW)];
-                        const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v), tag = (unsigned)(c / HRC + 1);
-                        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r_ll + (uint32_t)(c % HRC) * 16u), "r"(lo), "r"(tag),
-                                     "r"(hi), "r"(tag)
-                                     : "memory");
-                    }
-                } else if (c < upto) {
-                    if (remote)
-                        ll_store_sys(out + c, row[G::tcol(c % BW)], P.epoch);
-                    else
-                        ll_store(out + c, row[G::tcol(c % BW)], P.epoch);
-                }
-                sent = upto;
-                if (sent == blk_end) { // all 16 columns of this block are out: the stage may drain
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&done[blk % NST]);
+    for (int c0 = 0; c0 < ncols; c0 += HG) {
+        const int g = c0 / HG;
+        mbar_wait(&bell[g % NBELL], (unsigned)((g / NBELL) & 1), dead, P.scal);
+        const int blk = c0 / BW;
+        const double *row = last_row + (size_t)(blk % NST) * (STAGE_BYTES / 8);
+        const int c = c0 + lane;
+        double v = 0.0;
+        if (lane < HG) v = row[G::tcol(c % BW)];
+        if (dsmem) {
+            // ring slot c % HRC (and its group barrier) is free once the downstream strip's last row has
+            // passed column c - HRC; never asked after the downstream strip may have left
+            while (c0 + HG > HRC && down_progress < c0 + HG - HRC) {
+                down_progress = (int)ld_remote_u32(r_progress);
+                if (watch.expired(dead)) {
+                    *dead = 1;
+                    P.scal->watchdog = 1;
+                    break;
                 }
             }
-            watch = Watch();
-        } else if (watch.expired(dead)) {
-            *dead = 1;
-            P.scal->watchdog = 1;
-            for (int b = sent / BW; b < P.nbx; b++) // release every stage so that the other warps can finish
-                if (lane == 0) mbar_arrive(&done[b % NST]);
-            return;
+            if (lane < HG)
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
+                                 r_halo + (uint32_t)(c % HRC) * 8u),
+                             "l"(__double_as_longlong(v)), "r"(r_hb + (uint32_t)(g % NHB) * 8u)
+                             : "memory");
+        } else if (lane < HG) {
+            if (remote)
+                ll_store_sys(out + c, v, P.epoch);
+            else
+                ll_store(out + c, v, P.epoch);
+        }
+        if ((c0 + HG) % BW == 0) { // all 16 columns of this block are out: the stage may drain
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[blk % NST]);
         }
     }
 }
 
 // ---------------------------------------------------------------------- kernel ----
 template <bool BWD, bool DOT, bool MASKED>
-__global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParams P) {
+__global__ void __launch_bounds__(224, 1) k_tri(const __grid_constant__ TriParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[3 * NST]; // full[], done[], empty[]
+    __shared__ uint64_t bell[NBELL];   // rung by the compute warp for every group its last row completes
+    __shared__ uint64_t hb[NHB];       // hand-off groups received from the cluster neighbour (tx bytes)
     __shared__ int s_ticket;
     __shared__ int s_dead;
     __shared__ unsigned s_counters[2]; // [0] columns finished by the last row, [1] hand-off columns received
-    double *halo_s = reinterpret_cast<double *>(smem + (size_t)NST * STAGE_BYTES); // [HRC]
-    uint4 *ll_ring = reinterpret_cast<uint4 *>(halo_s + HRC);                      // [HRC] messages from the cluster neighbour
+    double *halo_s = reinterpret_cast<double *>(smem + (size_t)NST * STAGE_BYTES); // [HRC] upstream last-row values
     uint64_t *full = bars, *done = bars + NST, *empty = bars + 2 * NST;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned rank = P.cs > 1 ? cluster_ctarank() : 0;
@@ -493,14 +536,19 @@ __global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParam
         if (rank == 0) s_ticket = (int)(atomicAdd(P.ticket, 1ULL) - P.ticket_base);
         s_dead = 0;
         s_counters[0] = 0;
-        s_counters[1] = 0;
+        s_counters[1] = (TRI_EXP & 2) ? (1u << 30) : 0u;
+        // the barriers a cluster neighbour may touch exist (and are armed) before the cluster barrier
+        for (int i = 0; i < NHB; i++) {
+            mbar_init(&hb[i], 1);
+            mbar_arrive_expect_tx(&hb[i], HG * 8);
+        }
+        for (int i = 0; i < NBELL; i++) mbar_init(&bell[i], 1);
+        fence_mbar_init();
     }
-    if (P.cs > 1)
-        for (int i = threadIdx.x; i < HRC; i += blockDim.x) ll_ring[i] = make_uint4(0u, 0u, 0u, 0u); // tag 0 = empty
     __syncthreads();
     int ticket;
     if (P.cs > 1) {
-        cluster_sync_all(); // every CTA of the cluster is resident, its rings are clear, rank 0's ticket is set
+        cluster_sync_all(); // every CTA of the cluster is resident, its barriers are armed, rank 0's ticket is set
         ticket = (int)ld_remote_u32(mapa(smem_u32(&s_ticket), 0));
     } else {
         ticket = s_ticket;
@@ -509,7 +557,7 @@ __global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParam
     if (sj >= P.sj_base + P.nloc) return; // padding CTA of the last cluster
     if (P.gated && P.scal->done) return;  // the solve has converged
     if (threadIdx.x == 0) {
-        const bool publish = sj + 1 < P.nby;
+        const bool publish = sj + 1 < P.nby && !(TRI_EXP & 512);
         for (int i = 0; i < NST; i++) {
             mbar_init(&full[i], 1);               // loader's expect_tx arrival (+ TMA bytes)
             mbar_init(&done[i], publish ? 2 : 1); // compute warp (+ publisher warp)
@@ -525,7 +573,7 @@ __global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParam
         unsigned long long t0 = 0;
         const long long c0 = clock64();
         if (P.times && lane == 0) t0 = globaltimer_ns();
-        compute_warp<BWD>(P, smem, halo_s, full, done, sj, lane, &s_dead, s_counters);
+        compute_warp<BWD>(P, smem, halo_s, done, bell, sj, lane, &s_dead, s_counters);
         if (P.times && lane == 0) {
             P.times[16 * sj] = t0;
             P.times[16 * sj + 1] = globaltimer_ns();
@@ -535,13 +583,13 @@ __global__ void __launch_bounds__(192, 1) k_tri(const __grid_constant__ TriParam
         // (experiment: no helper warps)
     } else if (warp == 1) {
         loader_warp<BWD>(P, smem, full, empty, sj, lane, &s_dead);
-    } else if (warp == 2) {
-        storer_warp<BWD, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead);
+    } else if (warp == 2 || warp == 6) { // (warp 4 would share the compute warp's scheduler)
+        storer_warp<BWD, DOT, MASKED>(P, smem, done, empty, sj, lane, &s_dead, warp == 2 ? 0 : 1);
     } else if (warp == 3) {
-        if (sj + 1 < P.nby) publisher_warp<BWD>(P, smem, halo_s, done, sj, lane, &s_dead, s_counters, rank, ll_ring);
-    } else if (warp == 5 && sj > 0) {
+        if (sj + 1 < P.nby && !(TRI_EXP & 512)) publisher_warp<BWD>(P, smem, halo_s, done, bell, hb, sj, lane, &s_dead, s_counters, rank);
+    } else if (warp == 5) {
         // first strip of a cluster (and of a rank): its upstream strip talks through L2 / NVLink
-        poller_warp<BWD>(P, halo_s, sj, lane, &s_dead, s_counters, (rank == 0 || sj == P.sj_base) ? nullptr : ll_ring);
+        gatekeeper_warp<BWD>(P, halo_s, full, (rank == 0 || sj == P.sj_base) ? nullptr : hb, sj, lane, &s_dead, s_counters);
     }
 }
 
@@ -592,9 +640,9 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
     P.times = c->sweep_times;
     if (DOT) {
         P.partials = partials_next(c);
-        c->n_partials = P.nby;
+        c->n_partials = 2 * P.nby; // one per storer warp
     }
-    const size_t smem = (size_t)NST * STAGE_BYTES + (size_t)HRC * sizeof(double) + (size_t)HRC * sizeof(uint4);
+    const size_t smem = (size_t)NST * STAGE_BYTES + (size_t)HRC * sizeof(double);
     const bool masked = c->version >= 4;
     static bool attr_set[IFL_MAX_DEVICES][2][2][2]; // function attributes are per device
     auto kern = masked ? k_tri<BWD, DOT, true> : k_tri<BWD, DOT, false>;
@@ -607,7 +655,7 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(n_clusters * P.cs));
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(224);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];

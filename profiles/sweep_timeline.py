@@ -17,7 +17,11 @@ s.buildPreconditioner()
 s.set("r", np.random.default_rng(0).uniform(-1, 1, n * nh))
 for _ in range(3):
     s.applyPreconditioner("z", "r")
-t = s.sweep_times(lambda: s.applyPreconditioner("z", "r")).astype(np.int64)
+# third argument "dot": time the backward sweep WITH the fused z.r (the variant the PCG loop runs)
+if len(sys.argv) > 3 and sys.argv[3] == "dot":
+    t = s.sweep_times(lambda: s.project(2)).astype(np.int64)
+else:
+    t = s.sweep_times(lambda: s.applyPreconditioner("z", "r")).astype(np.int64)
 t0 = t[:, 0].min()
 start, end = t[:, 0] - t0, t[:, 1] - t0
 dur = end - start
@@ -31,6 +35,9 @@ print("strip 0: %.1f SM cycles/step, SM clock during the sweep %.0f MHz" % (t[0,
 print("end-to-end lag between consecutive strips (us): mean %.2f  min %.2f  max %.2f" %
       (np.diff(end).mean() / 1e3, np.diff(end).min() / 1e3, np.diff(end).max() / 1e3))
 print("start lag (us): mean %.2f" % (np.diff(start).mean() / 1e3))
+big = [(i + 1, round(float(x) / 1e3, 1)) for i, x in enumerate(np.diff(end)) if x > 2 * np.median(np.diff(end))]
+print("lags above twice the median (strip, us):", big[:24])
+print("median lag %.2f us" % (np.median(np.diff(end)) / 1e3))
 for i in list(range(0, len(t), max(1, len(t) // 16))):
     print("  strip %3d start %8.1f end %8.1f dur %8.1f us" % (i, start[i] / 1e3, end[i] / 1e3, dur[i] / 1e3))
 print("checkpoints (us since kernel start) for the first strips:")

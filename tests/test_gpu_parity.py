@@ -193,6 +193,20 @@ def test_add_inflow_bit_exact(ifl, port, version):
     dev.close()
 
 
+@pytest.mark.parametrize("version", [2, 3])
+def test_add_inflow_wraps_rows_on_tall_grids(ifl, port, version):
+    """w < h: the reference clamps the x loop with _h (v2:195), so a wide rectangle runs past the row and
+    its dense index x + y*_w lands in the following rows.  The device reproduces that wrap."""
+    w, h = 40, 100
+    dev, ora = make_pair(ifl, port, version, w, h, seed=8)
+    for s in (dev, ora):
+        s.addInflow(0.5, 0.3, 1.0, 0.4, 1.0, -0.5, 2.0)   # ix1 = 59 > w: 19 cells of every row wrap into the next
+        s.addInflow(0.1, 1.0, 2.4, 0.2, 0.7, 0.3, -1.0)   # ix1 = 99: wraps twice
+    for k in "duv":
+        assert_bits(dev.get(k + ".src"), ora.src[k], "addInflow (wrapped) " + k)
+    dev.close()
+
+
 # -------------------------------------------------------------- Gauss-Seidel -----
 @pytest.mark.parametrize("w,h", [(32, 32), (33, 35), (64, 96), (100, 70)])
 def test_gauss_seidel_sweeps_bit_exact(ifl, port, w, h):
