@@ -1,34 +1,47 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S] [--config C]
 
-A "step" is one FluidSolver::update() (buildRhs, buildPressureMatrix,
-buildPreconditioner, MIC(0)-PCG project with the reference's cap of 600 iterations,
-applyPressure, 3x advect, flip; v3:433-447) of a double-precision smoke plume with the
-shipped chapter-3 constants (v3:470-486) on an S x S grid (default 4096), preceded by
-the shipped addInflow call, all through the C ABI of libifl_b200.so.
+A "step" is one FluidSolver::update() of a double-precision smoke plume through the C ABI of
+libifl_b200.so, preceded by the shipped addInflow call.  The default workload is the one the
+metric is quoted on: chapter 3 at S x S = 4096^2 (buildRhs, buildPressureMatrix, buildPreconditioner,
+MIC(0)-PCG project with the reference's cap of 600 iterations, applyPressure, 3x advect, flip;
+v3:433-447, constants v3:470-486).  --config selects the other BASELINE.json workloads:
+    1  chapter 3, 128^2 (the reference's own CPU-runnable case)
+    2  chapter 2 at 2048^2: lexicographic Gauss-Seidel (limit 600), plus the PCG of chapter 3 on the same grid
+    3  chapter 5 at 4096^2, box + sphere + small box; the small box translates (SURVEY's rotating set makes
+       the unmodified reference diverge)
+    4  chapter 7 at 8192^2 (heat + variable density), row slabs on N GPUs (strong scaling: fixed grid)
+    5  chapter 8 (FLIP), 8 particles per cell; one GPU (the particle set is not sharded), 2048^2 by default
 
-metric   cell-updates/s = S*S*steps*N / time      (device-resident fields: `value`)
+metric   cell-updates/s = S*S*steps / time         (device-resident fields: `value`, profiling OFF)
 e2e      same metric through the host-buffer path: every step uploads d,u,v from pinned
          host memory, runs the step and downloads d,u,v (timed region includes copies)
-roofline per-kernel-class CUDA-event timing inside the timed region (ifl_profile);
-         the dominant class' algorithmic bytes / its mean launch time vs the measured
-         HBM copy bandwidth in MEASURED_PEAKS.json
+roofline a SEPARATE profiled pass (per-kernel-class CUDA events, ifl_profile) after the timed region:
+         the dominant class' algorithmic bytes / its mean launch time vs the measured HBM copy
+         bandwidth in MEASURED_PEAKS.json; `traffic` from the committed ncu capture of that kernel
 cpu_baseline  the reference's own CPU code (oracle/_ref if built, else the C port) on
          one host core, bounded sample, extrapolated per step (stated in `sample`)
+headline workload only:
+pcg_to_tolerance   one solve from the plume state with the cap lifted: iterations and time to |r|inf < 1e-5
+strong_16384       the north-star grid, 16384^2, on the N GPUs of this run (2 steps) and -- N > 1 -- on rank 0
+                   alone in the same invocation: speedup_vs_1gpu
+parity_vs_1gpu     N > 1: one 1024^2 step of chapters 3 and 5 on N slabs and on rank 0 alone, compared bit by bit
 
---impl reference runs only the CPU reference arm and prints the same JSON line.
-N > 1: one process per GPU (torchrun), ONE grid split into row slabs (SURVEY 8e,
-csrc/dist.cu): weak scaling, the grid grows with N so that every GPU keeps 4096^2 cells
-(side = 4096*sqrt(N) rounded to whole 32-row strips: 4096, 5792, 8192, 11584); the MIC(0)
-wavefront and the stencil rows cross slab boundaries over NVLink peer mappings, the
+--impl reference runs only the CPU reference arm and prints the same JSON line ("extrapolated": true: the
+per-step work outside the loop is timed once, every step then times a few more PCG iterations -- 3.5 s each
+at 4096^2 -- on the workload's own grid, and the step time is extrapolated to the loop's iteration count).
+N > 1: one process per GPU (torchrun), ONE grid split into row slabs (csrc/dist.cu): weak
+scaling, the grid grows with N so that every GPU keeps 4096^2 cells (side = 4096*sqrt(N) rounded to 32);
+the MIC(0) wavefront and the stencil rows cross slab boundaries over NVLink peer mappings, the
 reductions are folded identically on every rank.  Barrier + max-over-ranks timing.
 --size S overrides the side at any N (e.g. --size 16384 for the north-star grid).
 """
 import argparse
 import importlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -47,16 +60,19 @@ DT, DENSITY, LIMIT = 0.005, 0.1, 600              # v3:473-474, v3:437
 # once and each output written once.
 ALG_BYTES = {"matvec": 40, "axpy2_norm": 48, "precon_fwd": 40, "precon_bwd": 48, "xpay": 24,
              "advect": 80.0 / 3, "factor": 32, "gs_sweep": 24}
+# the kernel behind each class (as launched by ifl_project), for the ncu traffic lookup
+KERNEL_OF = {"precon_fwd": "k_tri<0,0,0>", "precon_bwd": "k_tri<1,1,0>", "matvec": "k_matvec<1>",
+             "axpy2_norm": "k_axpy2_norm", "xpay": "k_scaled_add<1>", "gs_sweep": "k_sweep<3,0,0>"}
 
 
-def ncu_traffic(kernel, size):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
-    ncu --set full capture (profiles/ncu_traffic.json), or None if it was taken at another size."""
+def ncu_traffic(cls, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind class `cls` from the
+    committed ncu --set full capture (profiles/ncu_traffic.json), or None if taken at another size."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
         if t["grid"] == [size, size]:
-            return t["bytes_per_launch"].get(kernel)
+            return t["bytes_per_launch"].get(KERNEL_OF.get(cls, cls))
     except Exception:
         pass
     return None
@@ -102,109 +118,248 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+# ----------------------------------------------------------------------- workloads ----
+def grid_side(args, n):
+    """Side of the square grid of the headline workload: 4096 on one GPU; with N GPUs 4096*sqrt(N)
+    rounded to 32, i.e. a constant 4096^2 cells per GPU (weak scaling)."""
+    if args.size:
+        return args.size
+    return int(round(4096 * n ** 0.5 / 32.0)) * 32
+
+
+BOX = (0, 0.5, 0.6, 0.7, 0.1, math.pi * 0.25, 0.0, 0.0, 0.0)  # the shipped box (v5:986, v7:1099, v8:1484)
+
+
+def workload(args, n):
+    """Everything that defines a run: chapter, grid, constants, bodies, inflow, what one step is."""
+    cfg = getattr(args, "config", "headline")
+    size = args.size
+    if cfg in ("headline", "1"):
+        s = size or (128 if cfg == "1" else grid_side(args, n))
+        return {"cfg": cfg, "version": 3, "size": s, "params": [DENSITY], "bodies": [], "inflow": INFLOW, "dt": DT,
+                "limit": LIMIT, "scaling": "weak" if (cfg == "headline" and not size) else "strong", "fields": "duv",
+                "name": "3-conjugate-gradients smoke plume %dx%d, double, MIC(0)-PCG limit %d, dt %.3f, "
+                        "inflow before every update (v3:470-486)" % (s, s, LIMIT, DT)}
+    if cfg == "2":
+        s = size or 2048
+        return {"cfg": cfg, "version": 2, "size": s, "params": [DENSITY], "bodies": [], "inflow": INFLOW, "dt": DT,
+                "limit": LIMIT, "scaling": "strong", "fields": "duv",
+                "name": "2-better-advection %dx%d, RK3 + Catmull-Rom advection, lexicographic Gauss-Seidel limit %d "
+                        "(v2:233-277, constants v2:353-380)" % (s, s, LIMIT)}
+    if cfg == "3":
+        s = size or 4096
+        bodies = [BOX, (1, 0.15, 0.3, 0.15, 0.15, 0.0, 0.0, 0.0, 0.0), (0, 0.85, 0.2, 0.2, 0.1, 0.0, 0.0, 0.02, 0.0)]
+        return {"cfg": cfg, "version": 5, "size": s, "params": [DENSITY], "bodies": bodies, "inflow": INFLOW, "dt": DT,
+                "limit": 2000, "scaling": "strong", "fields": "duv", "move_every": 4,
+                "name": "5-curved-boundaries %dx%d, box + sphere + translating small box (bodies updated every 4th "
+                        "step, v5:1011), MIC(0)-PCG with fractional volumes, limit 2000" % (s, s)}
+    if cfg == "4":
+        s = size or 8192
+        return {"cfg": cfg, "version": 7, "size": s, "params": [0.1, 1.0, 0.01], "bodies": [BOX],
+                "inflow": (0.45, 0.2, 0.1, 0.05, 1.0, None, 0.0, 0.0), "dt": DT, "limit": 2000, "scaling": "strong",
+                "fields": "dtuv", "move_every": 4,
+                "name": "7-variable-density %dx%d, heat + variable-density plume (v7:1084-1129), two MIC(0)-PCG solves "
+                        "per step, limit 2000" % (s, s)}
+    if cfg == "5":
+        s = size or 2048
+        return {"cfg": cfg, "version": 8, "size": s, "params": [0.1, 0.25, 0.01], "bodies": [BOX], "inflow": None,
+                "dt": 0.0025, "limit": 2000, "scaling": "strong", "fields": "dtuv", "avg_per_cell": 8,
+                "name": "8-flip %dx%d, 8 particles per cell (_AvgPerCell = 8), P2G + extrapolate + count/prune/seed, "
+                        "two MIC(0)-PCG solves, G2P, particle RK3 (v8:1350-1413)" % (s, s)}
+    raise SystemExit("bench.py: unknown --config %r" % cfg)
+
+
+def workload_config(wl, n):
+    size = wl["size"]
+    arrays = {2: 8, 3: 17, 5: 40, 7: 52, 8: 60}.get(wl["version"], 17)
+    return {"workload": wl["name"], "grid": [size, size], "pcg_limit": wl["limit"],
+            "parallelism": "1 GPU" if n == 1 else
+            "%d row slabs of one %dx%d grid, one process per GPU, peer-mapped HBM over NVLink, exact MIC(0) "
+            "pipelined across slabs" % (n, size, size),
+            "cells_per_gpu": size * size // n,
+            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (arrays * size * size * 8 / 1e9 / n)
+            if size >= 1024 else "working set fits the 126 MB L2 (config 1 is the reference's own small case; "
+                                 "latency-bound, no HBM roofline applies)"}
+
+
+def make_solver(ifl, wl, device=0, rank=0, world=1, rendezvous=None, size=None, version=None):
+    v = version or wl["version"]
+    s = size or wl["size"]
+    bodies = []
+    for b in (wl["bodies"] if v >= 4 else []):
+        bodies.append(ifl.SolidBox(*b[1:]) if b[0] == 0 else ifl.SolidSphere(b[1], b[2], b[3], *b[5:]))
+    p = wl["params"]
+    kw = {}
+    if v >= 6:
+        kw = {"rho_soot": p[1], "diffusion": p[2]}
+    if v >= 8:
+        kw["avg_per_cell"] = wl.get("avg_per_cell", 4)
+    return ifl.FluidSolver(s, s, p[0], version=v, device=device, bodies=bodies or None, rank=rank, world=world,
+                           rendezvous=rendezvous, **kw)
+
+
+def make_step(s, wl):
+    inflow, dt, state = wl["inflow"], wl["dt"], {"n": 0}
+    move_every = wl.get("move_every", 0)
+
+    def step():
+        if inflow is not None:
+            a = list(inflow)
+            if len(a) == 8 and a[5] is None:
+                a[5] = s.ambientT()
+            s.addInflow(*a)
+        st = s.update(dt)
+        state["n"] += 1
+        if move_every and state["n"] % move_every == 0:
+            for b in s.bodies:
+                b.update(dt)
+        return st
+    return step
+
+
 # ------------------------------------------------------------------ CPU reference ----
-CPU_SAMPLE_SIDE = 4096  # the CPU arm never times a grid larger than this (a 4096^2 sample already takes ~20 s)
+CPU_SAMPLE_SIDE = 4096  # the CPU arm never times a grid wider than this
 
 
-def cpu_reference_sample(full_size, cap_iters, full_iters):
-    """Times the reference's CPU path on a bounded sample of the workload: assembly +
-    project(limit=cap_iters) + applyPressure + 3x advect, one core, on a grid of at most
-    CPU_SAMPLE_SIDE^2 cells (every stage is a streaming pass far above the cache sizes, so the
-    time per cell does not depend on the grid; larger workloads are scaled by their cell count).
-    Returns (seconds per FULL step extrapolated to `full_iters` PCG iterations, detail)."""
-    from oracle import refapi
-    size = min(full_size, CPU_SAMPLE_SIDE)
-    cell_scale = (full_size / float(size)) ** 2
-    use_ref = refapi.available(3)
-    if use_ref:
-        s = refapi.Ref(3, size, size, [DENSITY])
-        call = s.call
-        ops = {"inflow": lambda: call("addInflow", *INFLOW), "rhs": lambda: call("buildRhs"),
-               "matrix": lambda: call("buildPressureMatrix", DT), "precon": lambda: call("buildPreconditioner"),
-               "project": lambda n: call("project", n), "pressure": lambda: call("applyPressure", DT),
-               "advect": lambda: [call(k + ".advect", DT) for k in "duv"]}
-        kind = "reference"
-    else:
-        from oracle import portapi
-        s = portapi.PortSolver(3, size, size, DENSITY)
-        ops = {"inflow": lambda: s.addInflow(*INFLOW), "rhs": s.buildRhs, "matrix": lambda: s.buildPressureMatrix(DT),
-               "precon": s.buildPreconditioner, "project": lambda n: s.project(n),
-               "pressure": lambda: s.applyPressure(DT), "advect": lambda: [s.advect(k, DT) for k in "duv"]}
-        kind = "port"
-    t = {}
+class CpuSampler:
+    """The reference's CPU path of workload `wl` on one core, on the workload's own grid (capped at
+    CPU_SAMPLE_SIDE^2 cells and scaled by the cell count beyond: the time per cell depends on the footprint --
+    a 4096 x 512 slice runs 8x faster per cell than 4096^2 -- so the sample is never a thinner slice).
+    setup() times everything that happens once per step (assembly, factorisation, the solve's prologue,
+    applyPressure, advection); sample(k) times k more PCG iterations (Gauss-Seidel sweeps for chapters 1-2)
+    on the same solver.  step_seconds() extrapolates to the iteration count of the device step."""
 
-    def timed(name, fn, *a):
+    def __init__(self, wl):
+        from oracle import refapi
+        self.wl = wl
+        v, full = wl["version"], wl["size"]
+        self.v = v
+        self.w = self.h = min(full, CPU_SAMPLE_SIDE)
+        self.cell_scale = (full * full) / float(self.w * self.h)
+        self.use_ref = refapi.available(v)
+        fields = wl["fields"]
+        dt = wl["dt"]
+        if self.use_ref:
+            s = self.s = refapi.Ref(v, self.w, self.h, wl["params"], wl["bodies"] if v >= 4 else ())
+            call = s.call
+            inflow = list(wl["inflow"]) if wl["inflow"] is not None else None
+            if inflow and len(inflow) == 8 and inflow[5] is None:
+                inflow[5] = call("ambientT")
+            ops = {"inflow": (lambda: call("addInflow", *inflow)) if inflow else (lambda: None),
+                   "rhs": lambda: call("buildRhs"), "pressure": lambda: call("applyPressure", dt),
+                   "advect": (lambda: [call(k + ".advect", dt) for k in fields]) if v <= 7 else (lambda: call("qs.advect", dt))}
+            if v >= 3:
+                ops.update({"matrix": lambda: call("buildPressureMatrix", dt), "precon": lambda: call("buildPreconditioner"),
+                            "project": lambda n: call("project", n)})
+            else:
+                ops.update({"matrix": lambda: None, "precon": lambda: None, "project": lambda n: call("project", n, dt)})
+            if v >= 4:
+                pre = ops["rhs"]
+                ops["rhs"] = lambda: ([call(k + ".fillSolidFields") for k in fields], pre())
+            if v >= 7:
+                m = ops["matrix"]
+                ops["matrix"] = lambda: (call("computeDensities"), m())
+            self.kind = "reference"
+        else:
+            if v > 3:
+                raise SystemExit("bench.py: oracle/_ref is not built and the C port covers chapters 1-3 only")
+            from oracle import portapi
+            s = self.s = portapi.PortSolver(v, self.w, self.h, wl["params"][0])
+            ops = {"inflow": lambda: s.addInflow(*wl["inflow"]), "rhs": s.buildRhs,
+                   "matrix": (lambda: s.buildPressureMatrix(dt)) if v >= 3 else (lambda: None),
+                   "precon": s.buildPreconditioner if v >= 3 else (lambda: None),
+                   "project": (lambda n: s.project(n)) if v >= 3 else (lambda n: s.project(n, dt)),
+                   "pressure": lambda: s.applyPressure(dt), "advect": lambda: [s.advect(k, dt) for k in "duv"]}
+            self.kind = "port"
+        self.ops = ops
+        self.t = {}
+        self.iter_samples = []
+
+    def _timed(self, name, fn, *a):
         t0 = time.perf_counter()
         fn(*a)
-        t[name] = time.perf_counter() - t0
+        self.t[name] = time.perf_counter() - t0
 
-    ops["inflow"]()
-    timed("rhs", ops["rhs"])
-    timed("matrix", ops["matrix"])
-    timed("precon", ops["precon"])
-    timed("project0", ops["project"], 0)          # prologue only (one applyPreconditioner, norm, dot)
-    ops["rhs"]()
-    timed("projectN", ops["project"], cap_iters)  # prologue + cap_iters iterations
-    timed("pressure", ops["pressure"])
-    timed("advect", ops["advect"])
-    per_iter = max(t["projectN"] - t["project0"], 1e-9) / max(cap_iters, 1)
-    fixed = t["rhs"] + t["matrix"] + t["precon"] + t["project0"] + t["pressure"] + t["advect"]
-    step = (fixed + per_iter * full_iters) * cell_scale
-    detail = ("%s CPU code, 1 thread, %dx%d: assembly+prologue+applyPressure+3 advects timed in full (%.2f s), "
-              "%d PCG iterations timed (%.3f s/iter), extrapolated to the %d iterations of the device step"
-              % ("unmodified reference (oracle/_ref)" if use_ref else "C port of the reference (oracle/ifl_oracle.c)",
-                 size, size, fixed, cap_iters, per_iter, full_iters))
-    if cell_scale != 1.0:
-        detail += "; scaled by %.2f (cells of the %dx%d workload / cells of the sample)" % (cell_scale, full_size, full_size)
-    if use_ref:
-        s.close()
-    return step, kind, detail
+    def setup(self):
+        o = self.ops
+        o["inflow"]()
+        self._timed("rhs", o["rhs"])
+        self._timed("matrix", o["matrix"])
+        self._timed("precon", o["precon"])
+        self._timed("project0", o["project"], 0)  # prologue only (one applyPreconditioner, norm, dot)
+        self._timed("pressure", o["pressure"])
+        self._timed("advect", o["advect"])
+        t = self.t
+        self.fixed = t["rhs"] + t["matrix"] + t["precon"] + t["project0"] + t["pressure"] + t["advect"]
+
+    def sample(self, k):
+        """k more iterations of the solve from a fresh right-hand side; returns seconds per iteration."""
+        self.ops["rhs"]()
+        t0 = time.perf_counter()
+        self.ops["project"](k)
+        per_iter = max(time.perf_counter() - t0 - self.t["project0"], 1e-9) / max(k, 1)
+        self.iter_samples.append((k, per_iter))
+        return per_iter
+
+    def step_seconds(self, per_iter, full_iters):
+        return (self.fixed + per_iter * full_iters) * self.cell_scale
+
+    def detail(self, full_iters):
+        what = "PCG iterations" if self.v >= 3 else "Gauss-Seidel sweeps"
+        n = sum(k for k, _ in self.iter_samples)
+        mean = sum(k * p for k, p in self.iter_samples) / max(n, 1)
+        d = ("%s CPU code of chapter %d, 1 thread, %dx%d: assembly+prologue+applyPressure+advection timed in full once (%.2f s), "
+             "%d %s timed in %d sample(s) (%.3f s each on average), extrapolated to the %d of the device step"
+             % ("unmodified reference (oracle/_ref)" if self.use_ref else "C port of the reference (oracle/ifl_oracle.c)",
+                self.v, self.w, self.h, self.fixed, n, what, len(self.iter_samples), mean, full_iters))
+        if self.v >= 6:
+            d += " (pressure solve only: the heat solve's handful of iterations and the particle transfers are not sampled)"
+        if self.cell_scale != 1.0:
+            d += "; scaled by %.2f (cells of the %dx%d workload / cells of the sample)" % (self.cell_scale, self.wl["size"], self.wl["size"])
+        return d
+
+    def close(self):
+        if self.use_ref:
+            self.s.close()
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = grid_side(args, args.gpus)
-    cap = min(args.cpu_iters, 3)  # ~18 s per sampled step: W + K steps end within a few minutes
+    wl = workload(args, args.gpus)
+    size = wl["size"]
+    cpu = CpuSampler(wl)
+    cpu.setup()
+    per_step_iters = 4 if min(size, CPU_SAMPLE_SIDE) >= 2048 else 10  # ~3.5 s per iteration at 4096^2
     times = []
-    kind = detail = None
     for i in range(args.warmup + args.steps):
-        step, kind, detail = cpu_reference_sample(size, cap, LIMIT)
+        per_iter = cpu.sample(per_step_iters)
         if i >= args.warmup:
-            times.append(step)
+            times.append(cpu.step_seconds(per_iter, wl["limit"]))
     mean = float(np.mean(times))
     value = size * size / mean
     line = {"impl": "reference", "metric": "cell-updates/sec (advect+PCG project)", "value": value,
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(size, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind, "sample": detail},
+            "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "extrapolated": True,
+            "config": workload_config(wl, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": cpu.kind,
+                             "sample": cpu.detail(wl["limit"])},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cpu.close()
     print(json.dumps(line))
 
 
-def grid_side(args, n):
-    """Side of the square grid: 4096 on one GPU; with N GPUs 4096*sqrt(N) rounded to whole
-    32-row strips, i.e. a constant 4096^2 cells per GPU (weak scaling)."""
-    if args.size:
-        return args.size
-    return int(round(4096 * n ** 0.5 / 32.0)) * 32
-
-
-def workload_config(size, n):
-    return {"workload": "3-conjugate-gradients smoke plume %dx%d, double, MIC(0)-PCG limit %d, dt %.3f, "
-                        "inflow before every update (v3:470-486)" % (size, size, LIMIT, DT),
-            "grid": [size, size], "pcg_limit": LIMIT,
-            "parallelism": "1 GPU" if n == 1 else
-            "%d row slabs of one %dx%d grid, one process per GPU, peer-mapped HBM over NVLink, exact MIC(0) "
-            "pipelined across slabs" % (n, size, size),
-            "cells_per_gpu": size * size // n,
-            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (17 * size * size * 8 / 1e9 / n)}
-
-
 # ------------------------------------------------------------------------- ours ----
+def fnv64(arrs):
+    h = 0xcbf29ce484222325
+    for a in arrs:
+        for wd in np.ascontiguousarray(a).view(np.uint64).ravel()[::97].tolist():  # every 97th word: a fingerprint, not a proof
+            h = ((h ^ wd) * 0x100000001b3) & ((1 << 64) - 1)
+    return "%016x" % h
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -219,125 +374,229 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ifl = importlib.import_module("incremental-fluids_b200")
-    size = grid_side(args, world)
-    rdv = "/tmp/ifl_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"))
-    s = ifl.FluidSolver(size, size, DENSITY, version=3, device=local, rank=rank, world=world, rendezvous=rdv)
-    stream = torch.cuda.ExternalStream(s.stream(), device=local)
+    wl = workload(args, world)
+    size, fields = wl["size"], wl["fields"]
+    if wl["version"] >= 8 and world > 1:
+        raise SystemExit("bench.py: config 5 runs on one GPU (the chapter-8 particle set is not sharded)")
+    rdv_base = "/tmp/ifl_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"))
 
-    def barrier():
-        s.sync()
+    def barrier(*solvers):
+        for x in solvers:
+            x.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    def step():
-        s.addInflow(*INFLOW)
-        return s.update(DT)
+    def timed_steps(s, step, k):
+        """K steps bracketed by barrier + synchronize, device time of the solver's stream, max over ranks."""
+        stream = torch.cuda.ExternalStream(s.stream(), device=local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(s)
+        ev0.record(stream)
+        out = [step() for _ in range(k)]
+        ev1.record(stream)
+        barrier(s)
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, out
 
+    s = make_solver(ifl, wl, local, rank, world, rdv_base)
+    step = make_step(s, wl)
     for _ in range(args.warmup):
         step()
-    barrier()
+    barrier(s)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # ---- timed region 1: device-resident steps, per-kernel-class events on
-    s.profile(True)
+    # ---- timed region 1: device-resident steps, NO per-launch events
     launches0 = s.launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    iters = []
-    for _ in range(args.steps):
-        iters.append(step()[1])
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms, stats = timed_steps(s, step, args.steps)
     launches = s.launches() - launches0
-    prof = s.profile_read()
-    s.profile(False)
+    iters = [st[1] for st in stats]
 
     # ---- timed region 2: end to end through host buffers (pinned), copies included
     # every rank keeps the rows of its own slab in pinned host memory (one GPU: whole fields)
-    host = {k: torch.empty(s.slab_elems(k + ".src"), dtype=torch.float64).pin_memory() for k in "duv"}
-    np_host = {k: v.numpy() for k, v in host.items()}
-    r0, r1 = s.rows()
-    for k in "duv":
-        full = s.get(k + ".src")
-        w_k = size + 1 if k == "u" else size
-        np_host[k][:] = full[r0 * w_k: r0 * w_k + np_host[k].size]
-        del full
-
-    def step_e2e():
+    e2e = None
+    if wl["version"] <= 7:
+        host = {k: torch.empty(s.slab_elems(k + ".src"), dtype=torch.float64).pin_memory() for k in "duv"}
+        np_host = {k: v.numpy() for k, v in host.items()}
+        r0, _ = s.rows()
         for k in "duv":
-            s.set_slab(k + ".src", np_host[k])
-        s.addInflow(*INFLOW)
-        s.update(DT)
-        for k in "duv":
-            s.get_slab(k + ".src", np_host[k])
+            full = s.get(k + ".src")
+            w_k = size + 1 if k == "u" else size
+            np_host[k][:] = full[r0 * w_k: r0 * w_k + np_host[k].size]
+            del full
 
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+        def step_e2e():
+            for k in "duv":
+                s.set_slab(k + ".src", np_host[k])
+            st = step()
+            for k in "duv":
+                s.get_slab(k + ".src", np_host[k])
+            return st
+
         step_e2e()
-    e1.record(stream)
-    barrier()
-    ms_e2e_dev = e0.elapsed_time(e1)
-    ms_e2e_wall = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(ms_e2e_dev, ms_e2e_wall)  # host-synchronous copies: wall clock is the honest one
+        barrier(s)
+        t0 = time.perf_counter()
+        ms_e2e_dev, _ = timed_steps(s, step_e2e, args.steps)
+        ms_e2e_wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e_dev, ms_e2e_wall)  # host-synchronous copies: wall clock is the honest one
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t[0])
+        bytes_io = sum(v.numel() * 8 for v in host.values()) * world
+        e2e = (ms_e2e, bytes_io)
     clocks = sampler.summary() if sampler else None
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- separate pass: per-kernel-class CUDA events (they cost ~3 % of a step, so they stay out of `value`)
+    s.profile(True)
+    prof_steps = min(args.steps, 2)
+    for _ in range(prof_steps):
+        step()
+    barrier(s)
+    prof = s.profile_read()
+    s.profile(False)
+
+    # ---- headline extras
+    extras = {}
+    if wl["cfg"] == "headline" and not args.no_extras:
+        # (d) the same plume state, cap lifted: project to |r|inf < 1e-5 (north_star), v3:349-380
+        s.addInflow(*INFLOW)
+        s.buildRhs()
+        s.buildPressureMatrix(DT)
+        s.buildPreconditioner()
+        barrier(s)
+        stream = torch.cuda.ExternalStream(s.stream(), device=local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        st = s.project(20000)
+        ev1.record(stream)
+        barrier(s)
+        ms_tol = ev0.elapsed_time(ev1)
+        extras["pcg_to_tolerance"] = {"tolerance": 1e-5, "converged": st[0] == 0, "iterations": st[1] + (1 if st[0] == 0 else 0),
+                                      "max_error": st[2], "ms": ms_tol,
+                                      "note": "the reference stops at its cap of 600 (v3:437) long before; iterations = the "
+                                              "zero-based count the reference prints + 1"}
+    s.close()
+    del s
+
+    if wl["cfg"] == "headline" and not args.no_extras and not args.size:
+        # (c) the north-star grid on the GPUs of this run
+        big = dict(wl, size=16384, name=wl["name"].replace("%dx%d" % (size, size), "16384x16384"))
+        sb = make_solver(ifl, big, local, rank, world, rdv_base + "_big")
+        stepb = make_step(sb, big)
+        stepb()
+        ms_big, _ = timed_steps(sb, stepb, 2)
+        sb.close()
+        del sb
+        blk = {"grid": [16384, 16384], "steps": 2, "ms_per_step": ms_big / 2, "value": 16384 * 16384 * 2 / (ms_big * 1e-3),
+               "unit": "cell-updates/s", "n_gpus": world}
+        if world > 1:
+            # the same grid on rank 0 alone, same invocation (the other ranks wait at the barrier)
+            one = None
+            if rank == 0:
+                s1 = make_solver(ifl, big, local)
+                step1 = make_step(s1, big)
+                step1()
+                stream = torch.cuda.ExternalStream(s1.stream(), device=local)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s1.sync()
+                ev0.record(stream)
+                step1()
+                ev1.record(stream)
+                s1.sync()
+                torch.cuda.synchronize()
+                one = ev0.elapsed_time(ev1)
+                s1.close()
+                del s1
+            dist.barrier()
+            if rank == 0:
+                blk["ms_per_step_1gpu"] = one
+                blk["speedup_vs_1gpu"] = one / (ms_big / 2)
+        else:
+            blk["speedup_vs_1gpu"] = 1.0
+        extras["strong_16384"] = blk
+
+    if world > 1 and not args.no_extras:
+        # driver-visible multi-GPU parity: one 1024^2 step of chapters 3 and 5 on N slabs vs rank 0 alone
+        par = {"bit_identical": True, "cases": []}
+        for ver, cfg in ((3, "headline"), (5, "3")):
+            class A:
+                size = 1024
+                config = cfg
+            w2 = workload(A, world)
+            sd = make_solver(ifl, w2, local, rank, world, rdv_base + "_p%d" % ver)
+            st_d = make_step(sd, w2)()
+            got = [sd.get(k + ".src") for k in "duv"]  # collective: every rank receives the whole arrays
+            sd.close()
+            if rank == 0:
+                s1 = make_solver(ifl, w2, local)
+                st_1 = make_step(s1, w2)()
+                want = [s1.get(k + ".src") for k in "duv"]
+                s1.close()
+                same = all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for a, b in zip(got, want)) and st_d[:2] == st_1[:2]
+                par["cases"].append({"chapter": ver, "grid": [1024, 1024], "bit_identical": bool(same), "iterations": st_d[1],
+                                     "fnv64": fnv64(got), "fnv64_1gpu": fnv64(want)})
+                par["bit_identical"] = par["bit_identical"] and bool(same)
+            dist.barrier()
+        extras["parity_vs_1gpu"] = par
 
     if rank == 0:
         cells = size * size
         value = cells * args.steps / (ms * 1e-3)  # the grid is ONE job over all ranks
-        e2e_value = cells * args.steps / (ms_e2e * 1e-3)
         peak, peak_src = measured_peak()
         shares = {k: v[0] for k, v in prof.items() if v[1] > 0}
         total_prof = sum(shares.values())
-        alg = dict(ALG_BYTES)
-        if "axpy2_norm" not in shares:  # p += alpha s, r -= alpha q, |r|inf ride inside the forward sweep
-            alg["precon_fwd"] = ALG_BYTES["precon_fwd"] + ALG_BYTES["axpy2_norm"]
-        dom = max((k for k in shares if k in alg), key=lambda k: shares[k])
+        dom = max((k for k in shares if k in ALG_BYTES), key=lambda k: shares[k])
         dom_ms, dom_n = prof[dom]
-        achieved = alg[dom] * cells / world / (dom_ms / dom_n * 1e-3) / 1e9  # per GPU (rank 0's launches)
-        # whole-iteration roofline: 200 algorithmic bytes per cell per PCG iteration
-        pcg_ms = sum(prof[k][0] for k in ("matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "scalar") if k in prof)
-        n_iter = prof["matvec"][1]
-        iter_gbs = 200.0 * cells * n_iter / (pcg_ms * 1e-3) / 1e9 if n_iter else None
-        bytes_io = sum(v.numel() * 8 for v in host.values()) * world
+        achieved = ALG_BYTES[dom] * cells / world / (dom_ms / dom_n * 1e-3) / 1e9  # per GPU (rank 0's launches)
         line = {
             "metric": "cell-updates/sec (advect+PCG project)", "value": value, "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(size, world),
-            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_io,
-                    "d2h_bytes_per_step": bytes_io, "ms_per_step": ms_e2e / args.steps},
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(wl, world),
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(dom, size) if world == 1 else None,
-                         "algorithmic_bytes_per_launch": alg[dom] * cells / world, "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell": alg[dom], "mean_launch_ms": dom_ms / dom_n,
-                         "share_of_profiled_time": dom_ms / total_prof if total_prof else None},
-            "pcg": {"iterations_per_step": iters, "iters_per_s": n_iter / (pcg_ms * 1e-3) if n_iter else None,
-                    "algorithmic_gbs_200B_per_cell_iter": iter_gbs,
-                    "frac_of_peak": iter_gbs / (peak * world) if iter_gbs else None},
+            "roofline": {"bound": "hbm", "kernel": dom, "kernel_name": KERNEL_OF.get(dom, dom), "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom, size) if world == 1 else None,
+                         "algorithmic_bytes_per_launch": ALG_BYTES[dom] * cells / world, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell": ALG_BYTES[dom], "mean_launch_ms": dom_ms / dom_n,
+                         "share_of_profiled_time": dom_ms / total_prof if total_prof else None,
+                         "measured_in": "separate pass of %d profiled step(s) after the timed region" % prof_steps},
             "kernel_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof.items() if v[1] > 0},
         }
+        if e2e:
+            line["e2e"] = {"value": cells * args.steps / (e2e[0] * 1e-3), "unit": "cell-updates/s",
+                           "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[1], "ms_per_step": e2e[0] / args.steps}
+        else:
+            line["e2e"] = {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "chapter 8 keeps its particle set on the device; the host-buffer entry point covers chapters 1-7"}
+        if wl["version"] >= 3:
+            # whole-iteration roofline: 200 algorithmic bytes per cell per PCG iteration (SURVEY 8d)
+            pcg_ms = sum(prof[k][0] for k in ("matvec", "axpy2_norm", "precon_fwd", "precon_bwd", "xpay", "scalar") if k in prof)
+            n_iter = prof["matvec"][1] if "matvec" in prof else 0
+            iter_gbs = 200.0 * cells * n_iter / (pcg_ms * 1e-3) / 1e9 if n_iter else None
+            line["pcg"] = {"iterations_per_step": iters, "iters_per_s": n_iter / (pcg_ms * 1e-3) if n_iter else None,
+                           "algorithmic_gbs_200B_per_cell_iter": iter_gbs,
+                           "frac_of_peak": iter_gbs / (peak * world) if iter_gbs else None}
+        else:
+            gs = prof.get("gs_sweep", (0.0, 0))
+            line["gauss_seidel"] = {"sweeps_per_step": iters, "sweeps_per_s": gs[1] / (gs[0] * 1e-3) if gs[1] else None}
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            step_s, kind, detail = cpu_reference_sample(size, args.cpu_iters, int(np.mean(iters)))
-            line["cpu_baseline"] = {"value": cells / step_s, "unit": "cell-updates/s", "cores": 1, "kind": kind,
-                                    "sample": detail}
+            full_iters = int(np.mean(iters)) if iters else wl["limit"]
+            cpu = CpuSampler(wl)
+            cpu.setup()
+            step_s = cpu.step_seconds(cpu.sample(args.cpu_iters), full_iters)
+            line["cpu_baseline"] = {"value": cells / step_s, "unit": "cell-updates/s", "cores": 1, "kind": cpu.kind,
+                                    "sample": cpu.detail(full_iters)}
+            cpu.close()
         print(json.dumps(line))
-    s.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,9 +607,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=0, help="grid side (default: 4096*sqrt(gpus), whole strips)")
-    ap.add_argument("--cpu-iters", type=int, default=6, help="PCG iterations timed on the CPU sample")
+    ap.add_argument("--config", default="headline", choices=["headline", "1", "2", "3", "4", "5"])
+    ap.add_argument("--size", type=int, default=0, help="grid side (default: the workload's own; headline: 4096*sqrt(gpus))")
+    ap.add_argument("--cpu-iters", type=int, default=10, help="PCG iterations timed on the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip pcg_to_tolerance / strong_16384 / parity_vs_1gpu")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

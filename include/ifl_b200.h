@@ -204,14 +204,29 @@ int ifl_add_inflow_t(ifl_ctx *ctx, double x, double y, double w, double h, doubl
 
 /* ---- chapter 8: FLIP particle <-> grid transfers -------------------------------- */
 /* The particle set is ParticleQuantities' SoA (v8:717-723): posX, posY and one property
- * array per registered quantity in the order d, t, u, v (v8:1309-1312); capacity w*h*12.
- * Particle bookkeeping (init/count/prune/seed, v8:735-813) stays on the host side of this
- * boundary for now: upload the set, run the transfers on the device, download it. */
-int ifl_particles_capacity(const ifl_ctx *ctx);
-int ifl_particles_upload(ifl_ctx *ctx, int count, const double *pos_x, const double *pos_y, const double *prop_d,
+ * array per registered quantity in the order d, t, u, v (v8:1309-1312); capacity w*h*12
+ * (_MaxPerCell, v8:694, 869).  Counts are 64-bit: the reference's `int` overflows at 13378^2 cells. */
+long long ifl_particles_capacity(const ifl_ctx *ctx);
+long long ifl_particles_count(const ifl_ctx *ctx);
+/* What the two constructors do (v8:877, 1306-1314): initParticles (v8:735-751) on the jittered grid with
+ * `avg_per_cell` attempts per cell (_AvgPerCell, 4 as shipped), consuming the reference's frand stream
+ * (v8:38-46) from its seed, then gridToParticles(1.0).  Call once, after the bodies have been set. */
+int ifl_particles_init(ifl_ctx *ctx, int avg_per_cell);
+/* particlesToGrid (v8:916-927): per quantity fromParticles + extrapolate, then countParticles,
+ * pruneParticles, seedParticles (v8:754-813) with the same random stream, slot assignment and
+ * swap-with-last order as the sequential loops.  *count (may be NULL) = what "Particle count: %d" prints. */
+int ifl_particles_to_grid(ifl_ctx *ctx, long long *count);
+int ifl_count_particles(ifl_ctx *ctx);  /* v8:754-763 */
+int ifl_prune_particles(ifl_ctx *ctx);  /* v8:766-786 (needs ifl_count_particles) */
+int ifl_seed_particles(ifl_ctx *ctx);   /* v8:789-813 (needs the counts after pruning) */
+int ifl_particles_upload(ifl_ctx *ctx, long long count, const double *pos_x, const double *pos_y, const double *prop_d,
                          const double *prop_t, const double *prop_u, const double *prop_v);
-int ifl_particles_download(ifl_ctx *ctx, int *count, double *pos_x, double *pos_y, double *prop_d, double *prop_t,
+int ifl_particles_download(ifl_ctx *ctx, long long *count, double *pos_x, double *pos_y, double *prop_d, double *prop_t,
                            double *prop_u, double *prop_v);
+/* Test hook: raw slots [first, first + n) of posX (what = 0), posY (1), the four properties (2..5) -- including
+ * the stale slots past the count, which the reference's seedParticles may read (v8:802) -- or the per-cell
+ * counts as ints (6). */
+int ifl_particles_peek(ifl_ctx *ctx, int what, long long first, long long n, void *host);
 /* FluidQuantity::fromParticles (v8:663-688): P2G of one quantity, contributions summed in
  * ascending particle index like the reference; marks particle-free fluid cells CELL_EMPTY (2). */
 int ifl_from_particles(ifl_ctx *ctx, int field);

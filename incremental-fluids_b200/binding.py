@@ -47,7 +47,9 @@ EXPORTS = [
     "ifl_aux_elems", "ifl_aux_download", "ifl_aux_upload",
     "ifl_set_fluid_params", "ifl_ambient_t", "ifl_build_heat_matrix", "ifl_add_buoyancy", "ifl_compute_densities",
     "ifl_add_inflow_t",
-    "ifl_particles_capacity", "ifl_particles_upload", "ifl_particles_download", "ifl_from_particles",
+    "ifl_particles_capacity", "ifl_particles_count", "ifl_particles_init", "ifl_particles_to_grid",
+    "ifl_count_particles", "ifl_prune_particles", "ifl_seed_particles", "ifl_particles_peek",
+    "ifl_particles_upload", "ifl_particles_download", "ifl_from_particles",
     "ifl_grid_to_particles", "ifl_quantity_copy", "ifl_quantity_diff", "ifl_quantity_undiff", "ifl_particles_advect",
     "ifl_build_rhs", "ifl_build_pressure_matrix", "ifl_build_preconditioner", "ifl_apply_preconditioner",
     "ifl_matrix_vector_product", "ifl_dot_product", "ifl_scaled_add", "ifl_infinity_norm",
@@ -119,9 +121,19 @@ def load_library():
     L.ifl_add_buoyancy.argtypes = [vp, cd]
     L.ifl_compute_densities.argtypes = [vp]
     L.ifl_add_inflow_t.argtypes = [vp, cd, cd, cd, cd, cd, cd, cd, cd]
+    ll = ctypes.c_longlong
     L.ifl_particles_capacity.argtypes = [vp]
-    L.ifl_particles_upload.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
-    L.ifl_particles_download.argtypes = [vp, ctypes.POINTER(ci), vp, vp, vp, vp, vp, vp]
+    L.ifl_particles_capacity.restype = ll
+    L.ifl_particles_count.argtypes = [vp]
+    L.ifl_particles_count.restype = ll
+    L.ifl_particles_init.argtypes = [vp, ci]
+    L.ifl_particles_to_grid.argtypes = [vp, ctypes.POINTER(ll)]
+    L.ifl_count_particles.argtypes = [vp]
+    L.ifl_prune_particles.argtypes = [vp]
+    L.ifl_seed_particles.argtypes = [vp]
+    L.ifl_particles_peek.argtypes = [vp, ci, ll, ll, vp]
+    L.ifl_particles_upload.argtypes = [vp, ll, vp, vp, vp, vp, vp, vp]
+    L.ifl_particles_download.argtypes = [vp, ctypes.POINTER(ll), vp, vp, vp, vp, vp, vp]
     L.ifl_from_particles.argtypes = [vp, ci]
     L.ifl_grid_to_particles.argtypes = [vp, cd]
     L.ifl_quantity_copy.argtypes = [vp, ci]
@@ -207,13 +219,17 @@ class FluidSolver:
     """
 
     def __init__(self, w, h, density, version=3, device=0, bodies=None, rho_soot=None, diffusion=None,
-                 rank=0, world=1, rendezvous=None):
+                 rank=0, world=1, rendezvous=None, avg_per_cell=4, init_particles=True):
         """Chapters 1-5: FluidSolver(w, h, density[, bodies]).  Chapters 6-7:
         FluidSolver(w, h, rhoAir, rhoSoot, diffusion, bodies) (v6:921) -- pass rhoAir as
         `density` plus rho_soot= and diffusion=.
 
         world > 1: row-slab multi-GPU, one process per GPU (ifl_create_dist); `rendezvous` is
-        a UNIX socket path shared by the ranks.  Every method is then a collective call."""
+        a UNIX socket path shared by the ranks.  Every method is then a collective call.
+
+        Chapter 8: like the reference's constructors (v8:877, 1306-1314) this seeds the particle set on the
+        jittered grid (`avg_per_cell` = _AvgPerCell, v8:698) and interpolates the initial fields onto it;
+        init_particles=False leaves the set empty (tests that upload their own particles)."""
         self.L = load_library()
         self.w, self.h, self.density, self.version = w, h, density, version
         self.hx = 1.0 / min(w, h)
@@ -234,6 +250,8 @@ class FluidSolver:
         if version >= 6:
             self._chk(self.L.ifl_set_fluid_params(self.ctx, density, rho_soot, diffusion))
         self.last_heat = None
+        if version >= 8 and init_particles:
+            self.initParticles(avg_per_cell)
 
     # ---- chapter 8 (FLIP): ParticleQuantities' transfers
     def setParticles(self, posX, posY, props):
@@ -241,8 +259,37 @@ class FluidSolver:
         self._particles_keepalive = arrs
         self._chk(self.L.ifl_particles_upload(self.ctx, arrs[0].size, *[a.ctypes.data for a in arrs]))
 
+    def initParticles(self, avg_per_cell=4):
+        """What the reference's two constructors do (v8:877, 1306-1314): initParticles + gridToParticles(1.0)."""
+        self._chk(self.L.ifl_particles_init(self.ctx, avg_per_cell))
+
+    def particleCount(self):
+        return int(self.L.ifl_particles_count(self.ctx))
+
+    def particlesToGrid(self):
+        n = ctypes.c_longlong()
+        self._chk(self.L.ifl_particles_to_grid(self.ctx, ctypes.byref(n)))
+        self.messages.append("Particle count: %d" % n.value)  # v8:926
+        return n.value
+
+    def countParticles(self):
+        self._chk(self.L.ifl_count_particles(self.ctx))
+
+    def pruneParticles(self):
+        self._chk(self.L.ifl_prune_particles(self.ctx))
+
+    def seedParticles(self):
+        self._chk(self.L.ifl_seed_particles(self.ctx))
+
+    def peekParticles(self, what, first, n):
+        """Raw slots incl. the stale tail: what in posX, posY, d, t, u, v, counts."""
+        k = ["posX", "posY", "d", "t", "u", "v", "counts"].index(what)
+        out = np.empty(n, dtype=np.int32 if k == 6 else np.float64)
+        self._chk(self.L.ifl_particles_peek(self.ctx, k, first, n, out.ctypes.data))
+        return out
+
     def getParticles(self):
-        n = ctypes.c_int()
+        n = ctypes.c_longlong()
         self._chk(self.L.ifl_particles_download(self.ctx, ctypes.byref(n), None, None, None, None, None, None))
         out = [np.empty(n.value) for _ in range(6)]
         self._chk(self.L.ifl_particles_download(self.ctx, ctypes.byref(n), *[a.ctypes.data for a in out]))
@@ -465,6 +512,8 @@ class FluidSolver:
             self.syncBodies()
         infos = (SolveInfo * 2)()
         self._chk(self.L.ifl_update(self.ctx, timestep, self.density, infos))
+        if self.version >= 8:  # particlesToGrid prints first (v8:926), then the two solves
+            self.messages.append("Particle count: %d" % self.particleCount())
         return self._record_update(infos)
 
     def update_host(self, timestep, d, u, v):

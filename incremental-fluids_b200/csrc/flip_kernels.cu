@@ -17,43 +17,130 @@
 //      reference's two statements.  Result: bit-identical `src`, `weight` and cell flags.
 // Particle SoA (posX, posY, one array per quantity) is kept as in the reference (v8:717-723);
 // all particle kernels are coalesced one-thread-per-particle streams.
-#include "ifl_internal.cuh"
-#include "solid_geometry.cuh"
-
-#include <cub/device/device_scan.cuh>
+#include "flip_internal.cuh"
 
 namespace ifl {
 
-enum { CELL_EMPTY = 2 }; // v8:115-119
+// ------------------------------------------------------------------ prefix sums ----
+// Block-wise scan (1024 items per block), recursive scan of the block sums, add-back.  Plain kernels of
+// this library: no CUB on the path.
+constexpr int SCAN_ITEMS = 1024;
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_blocks(const T *__restrict__ in, long long *__restrict__ out, size_t n,
+                                                     long long *__restrict__ block_sums) {
+    __shared__ long long warp_tot[8];
+    const size_t base = (size_t)blockIdx.x * SCAN_ITEMS + (size_t)threadIdx.x * 4;
+    long long v[4], run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = base + k < n ? (long long)in[base + k] : 0;
+        run += v[k];
+    }
+    // inclusive scan of the per-thread totals: warp shuffle, then the 8 warp totals
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    long long before = 0;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    long long excl = before + incl - run;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = before + incl;
+}
+__global__ void __launch_bounds__(256) k_scan_add(long long *__restrict__ out, size_t n, const long long *__restrict__ block_offsets) {
+    const size_t i = (size_t)blockIdx.x * SCAN_ITEMS + threadIdx.x;
+    const long long add = block_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t j = i + (size_t)k * 256;
+        if (j < n) out[j] += add;
+    }
+}
+// one block scans up to a few million block sums in place (exclusive) and stores the grand total
+__global__ void __launch_bounds__(1024) k_scan_small(long long *__restrict__ a, size_t n, long long *__restrict__ total) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (size_t base = 0; base < n; base += 1024) {
+        const size_t i = base + threadIdx.x;
+        const long long v = i < n ? a[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        long long before = carry_s;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        if (i < n) a[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+int scan_exclusive(ifl_ctx *c, const int *in, long long *out, size_t n, long long *total_dev) {
+    ParticleSet *ps = (ParticleSet *)c->particles;
+    if (n == 0) {
+        if (total_dev) IFL_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(long long), c->stream));
+        return IFL_OK;
+    }
+    const size_t nblocks = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    if (nblocks > ps->scan_tmp_elems) {
+        set_error("scan_exclusive: %zu items exceed the scratch sized at flip_init", n);
+        return IFL_E_ARG;
+    }
+    k_scan_blocks<int><<<(unsigned)nblocks, 256, 0, c->stream>>>(in, out, n, ps->scan_tmp);
+    IFL_LAUNCHED(c);
+    k_scan_small<<<1, 1024, 0, c->stream>>>(ps->scan_tmp, nblocks, total_dev);
+    IFL_LAUNCHED(c);
+    k_scan_add<<<(unsigned)nblocks, 256, 0, c->stream>>>(out, n, ps->scan_tmp);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
 
 // ------------------------------------------------------------------- binning ----
 __global__ void __launch_bounds__(256) k_bin_count(const double *__restrict__ posX, const double *__restrict__ posY,
-                                                   int n, int w, int h, int *__restrict__ counts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   long long n, int w, int h, int *__restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = imin(imax((int)posX[i], 0), w - 1), cy = imin(imax((int)posY[i], 0), h - 1);
     atomicAdd(&counts[cx + cy * w], 1);
 }
 
 __global__ void __launch_bounds__(256) k_bin_scatter(const double *__restrict__ posX, const double *__restrict__ posY,
-                                                     int n, int w, int h, const int *__restrict__ offsets,
-                                                     int *__restrict__ fill, int *__restrict__ list) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                     long long n, int w, int h, const long long *__restrict__ offsets,
+                                                     int *__restrict__ fill, unsigned *__restrict__ list) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = imin(imax((int)posX[i], 0), w - 1), cy = imin(imax((int)posY[i], 0), h - 1);
     const int c = cx + cy * w;
-    list[offsets[c] + atomicAdd(&fill[c], 1)] = i;
+    list[offsets[c] + atomicAdd(&fill[c], 1)] = (unsigned)i;
 }
 
 // each bin ascending by particle index (bins hold a handful of particles: v8:694-698)
-__global__ void __launch_bounds__(256) k_bin_sort(const int *__restrict__ offsets, const int *__restrict__ counts,
-                                                  int ncells, int *__restrict__ list) {
+__global__ void __launch_bounds__(256) k_bin_sort(const long long *__restrict__ offsets, const int *__restrict__ counts,
+                                                  int ncells, unsigned *__restrict__ list) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
-    int *a = list + offsets[c];
+    unsigned *a = list + offsets[c];
     const int m = counts[c];
     for (int i = 1; i < m; i++) {
-        const int v = a[i];
+        const unsigned v = a[i];
         int j = i - 1;
         while (j >= 0 && a[j] > v) {
             a[j + 1] = a[j];
@@ -66,8 +153,8 @@ __global__ void __launch_bounds__(256) k_bin_sort(const int *__restrict__ offset
 // ----------------------------------------------------------------------- P2G ----
 __global__ void __launch_bounds__(128) k_from_particles(Field f, double *__restrict__ weight, int weight_pitch,
                                                         const double *__restrict__ posX, const double *__restrict__ posY,
-                                                        const double *__restrict__ prop, const int *__restrict__ offsets,
-                                                        const int *__restrict__ counts, const int *__restrict__ list,
+                                                        const double *__restrict__ prop, const long long *__restrict__ offsets,
+                                                        const int *__restrict__ counts, const unsigned *__restrict__ list,
                                                         int W, int H) {
     const int gx = blockIdx.x * 32 + (threadIdx.x & 31);
     const int gy = blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -75,7 +162,8 @@ __global__ void __launch_bounds__(128) k_from_particles(Field f, double *__restr
     // bins that can hold contributors of node (gx, gy)
     const int bx0 = imax(gx - 1, 0), bx1 = imin(gx + 1, W - 1);
     const int by0 = imax(gy - 1, 0), by1 = imin(gy + 1, H - 1);
-    int cur[9], end[9], nb = 0;
+    long long cur[9], end[9];
+    int nb = 0;
     for (int by = by0; by <= by1; by++)
         for (int bx = bx0; bx <= bx1; bx++) {
             const int c = bx + by * W;
@@ -86,11 +174,12 @@ __global__ void __launch_bounds__(128) k_from_particles(Field f, double *__restr
     const double xmax = f.w - 1.5, ymax = f.h - 1.5;
     double wsum = 0.0, vsum = 0.0; // memset(_src), memset(weight)  v8:664-665
     for (;;) {
-        int best = -1, bi = 0x7fffffff;
+        int best = -1;
+        unsigned bi = 0xffffffffu;
         for (int b = 0; b < nb; b++)
             if (cur[b] < end[b]) {
-                const int pi = list[cur[b]];
-                if (pi < bi) {
+                const unsigned pi = list[cur[b]];
+                if (best < 0 || pi < bi) {
                     bi = pi;
                     best = b;
                 }
@@ -120,24 +209,11 @@ __global__ void __launch_bounds__(128) k_from_particles(Field f, double *__restr
 }
 
 // ----------------------------------------------------------------------- G2P ----
-__device__ __forceinline__ double lerp1p(double a, double b, double x) { return a * (1.0 - x) + b * x; } // v8:289
-
-__device__ __forceinline__ double field_lerp(const Field &f, double x, double y) { // v8:390-402
-    x = std_min(std_max(x - f.ox, 0.0), f.w - 1.001);
-    y = std_min(std_max(y - f.oy, 0.0), f.h - 1.001);
-    const int ix = (int)x, iy = (int)y;
-    x -= ix;
-    y -= iy;
-    const double *p = f.src.p + ix + (size_t)iy * f.src.pitch;
-    const double x00 = p[0], x10 = p[1], x01 = p[f.src.pitch], x11 = p[f.src.pitch + 1];
-    return lerp1p(lerp1p(x00, x10, x), lerp1p(x01, x11, x), y);
-}
-
 // prop = prop*(1-alpha) + lerp(field)   v8:907-908, one launch per quantity (registration order)
 __global__ void __launch_bounds__(256) k_grid_to_particles(Field f, double *__restrict__ prop,
                                                            const double *__restrict__ posX,
-                                                           const double *__restrict__ posY, int n, double alpha) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                           const double *__restrict__ posY, long long n, double alpha) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double v = prop[i];
     v *= 1.0 - alpha;
@@ -158,10 +234,10 @@ __global__ void __launch_bounds__(256) k_diff(Arr src, Arr old, double one_minus
 }
 
 // ----------------------------------------------------------- particle advection ----
-__global__ void __launch_bounds__(256) k_particles_advect(double *__restrict__ posX, double *__restrict__ posY, int n,
+__global__ void __launch_bounds__(256) k_particles_advect(double *__restrict__ posX, double *__restrict__ posY, long long n,
                                                           Field u, Field v, double timestep, double hx, int W, int H,
                                                           const BodyDev *__restrict__ bodies, int nb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = posX[i], y = posY[i];
     // rungeKutta3, forward in time  v8:844-862 (third stage not divided by hx)
@@ -203,36 +279,40 @@ __global__ void __launch_bounds__(256) k_particles_advect(double *__restrict__ p
 }
 
 // -------------------------------------------------------------------- host side ----
-struct ParticleSet {
-    double *posX, *posY, *prop[4];
-    int count, capacity;
-    int *counts, *offsets, *fill, *list; // bins over the w*h base cells
-    void *scan_tmp;
-    size_t scan_bytes;
-    bool binned; // bins match the current positions
-    Arr weight;  // (w+1) x (h+1) scratch like ParticleQuantities::_weight v8:874
-};
-
 int flip_init(ifl_ctx *c) {
     ParticleSet *ps = (ParticleSet *)calloc(1, sizeof(ParticleSet));
     if (!ps) return IFL_E_NOMEM;
     c->particles = ps;
-    ps->capacity = c->W * c->H * 12; // _MaxPerCell v8:694, 869
+    ps->capacity = (long long)c->W * c->H * 12; // _MaxPerCell v8:694, 869 (64-bit: SURVEY quirk 14)
+    ps->avg_per_cell = 4;                       // _AvgPerCell v8:698
+    ps->draws = 0;
+    if (ps->capacity > 0xffffffffLL) {
+        set_error("ifl_create: %lld particle slots (w*h*12) exceed the 2^32 - 1 one rank can index; shard the grid over more GPUs",
+                  ps->capacity);
+        return IFL_E_ARG;
+    }
     const size_t nb = (size_t)ps->capacity * sizeof(double);
     IFL_CUDA(cudaMalloc(&ps->posX, nb));
     IFL_CUDA(cudaMalloc(&ps->posY, nb));
+    IFL_CUDA(cudaMemset(ps->posX, 0, nb)); // (`new double[]` of this size is a fresh zero mapping in the reference)
+    IFL_CUDA(cudaMemset(ps->posY, 0, nb));
     for (int t = 0; t < 4; t++) {
         IFL_CUDA(cudaMalloc(&ps->prop[t], nb));
         IFL_CUDA(cudaMemset(ps->prop[t], 0, nb)); // addQuantity v8:893-894
     }
     const size_t ncells = (size_t)c->W * c->H;
     IFL_CUDA(cudaMalloc(&ps->counts, ncells * sizeof(int)));
-    IFL_CUDA(cudaMalloc(&ps->offsets, ncells * sizeof(int)));
+    IFL_CUDA(cudaMalloc(&ps->offsets, ncells * sizeof(long long)));
     IFL_CUDA(cudaMalloc(&ps->fill, ncells * sizeof(int)));
-    IFL_CUDA(cudaMalloc(&ps->list, (size_t)ps->capacity * sizeof(int)));
-    ps->scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, ps->scan_bytes, ps->counts, ps->offsets, (int)ncells);
-    IFL_CUDA(cudaMalloc(&ps->scan_tmp, ps->scan_bytes));
+    IFL_CUDA(cudaMalloc(&ps->list, (size_t)ps->capacity * sizeof(unsigned)));
+    // flags / offsets of the bookkeeping passes: one per particle slot (>= one per init attempt, one per cell)
+    ps->flags_elems = (size_t)ps->capacity;
+    IFL_CUDA(cudaMalloc(&ps->flags, ps->flags_elems * sizeof(int)));
+    IFL_CUDA(cudaMalloc(&ps->flag_offsets, ps->flags_elems * sizeof(long long)));
+    ps->scan_tmp_elems = ps->flags_elems / SCAN_ITEMS + 2;
+    IFL_CUDA(cudaMalloc(&ps->scan_tmp, ps->scan_tmp_elems * sizeof(long long)));
+    IFL_CUDA(cudaMalloc(&ps->dev_scalars, 8 * sizeof(long long)));
+    IFL_CUDA(cudaMallocHost(&ps->host_scalars, 8 * sizeof(long long)));
     ps->weight.w = c->W + 1;
     ps->weight.h = c->H + 1;
     ps->weight.pitch = (c->W + 1 + 31) / 32 * 32;
@@ -245,29 +325,32 @@ int flip_init(ifl_ctx *c) {
 void flip_free(ifl_ctx *c) {
     ParticleSet *ps = (ParticleSet *)c->particles;
     if (!ps) return;
-    void *ptrs[] = {ps->posX,   ps->posY,    ps->prop[0], ps->prop[1], ps->prop[2],  ps->prop[3],
-                    ps->counts, ps->offsets, ps->fill,    ps->list,    ps->scan_tmp, ps->weight.p};
+    void *ptrs[] = {ps->posX,   ps->posY,    ps->prop[0], ps->prop[1], ps->prop[2],  ps->prop[3],  ps->counts,
+                    ps->offsets, ps->fill,   ps->list,    ps->scan_tmp, ps->weight.p, ps->flags,   ps->flag_offsets,
+                    ps->dev_scalars};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (ps->host_scalars) cudaFreeHost(ps->host_scalars);
     free(ps);
     c->particles = nullptr;
 }
 
-static int ensure_bins(ifl_ctx *c) {
+int ensure_bins(ifl_ctx *c) {
     ParticleSet *ps = (ParticleSet *)c->particles;
     if (ps->binned) return IFL_OK;
-    const int ncells = c->W * c->H, n = ps->count;
+    const int ncells = c->W * c->H;
+    const long long n = ps->count;
     IFL_CUDA(cudaMemsetAsync(ps->counts, 0, (size_t)ncells * sizeof(int), c->stream));
     IFL_CUDA(cudaMemsetAsync(ps->fill, 0, (size_t)ncells * sizeof(int), c->stream));
     if (n > 0) {
-        k_bin_count<<<(n + 255) / 256, 256, 0, c->stream>>>(ps->posX, ps->posY, n, c->W, c->H, ps->counts);
+        k_bin_count<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(ps->posX, ps->posY, n, c->W, c->H, ps->counts);
         IFL_LAUNCHED(c);
     }
-    IFL_CUDA(cub::DeviceScan::ExclusiveSum(ps->scan_tmp, ps->scan_bytes, ps->counts, ps->offsets, ncells, c->stream));
-    c->launches++;
+    int rc = scan_exclusive(c, ps->counts, ps->offsets, (size_t)ncells, nullptr);
+    if (rc != IFL_OK) return rc;
     if (n > 0) {
-        k_bin_scatter<<<(n + 255) / 256, 256, 0, c->stream>>>(ps->posX, ps->posY, n, c->W, c->H, ps->offsets, ps->fill,
-                                                              ps->list);
+        k_bin_scatter<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(ps->posX, ps->posY, n, c->W, c->H, ps->offsets, ps->fill,
+                                                                         ps->list);
         IFL_LAUNCHED(c);
         k_bin_sort<<<(ncells + 255) / 256, 256, 0, c->stream>>>(ps->offsets, ps->counts, ncells, ps->list);
         IFL_LAUNCHED(c);
@@ -276,10 +359,10 @@ static int ensure_bins(ifl_ctx *c) {
     return IFL_OK;
 }
 
-int flip_set_particles(ifl_ctx *c, int count, const double *posX, const double *posY, const double *const *props) {
+int flip_set_particles(ifl_ctx *c, long long count, const double *posX, const double *posY, const double *const *props) {
     ParticleSet *ps = (ParticleSet *)c->particles;
     if (count < 0 || count > ps->capacity) {
-        set_error("particle count %d exceeds the capacity w*h*12 = %d (v8:869)", count, ps->capacity);
+        set_error("particle count %lld exceeds the capacity w*h*12 = %lld (v8:869)", count, ps->capacity);
         return IFL_E_ARG;
     }
     const size_t nb = (size_t)count * sizeof(double);
@@ -287,13 +370,21 @@ int flip_set_particles(ifl_ctx *c, int count, const double *posX, const double *
     IFL_CUDA(cudaMemcpyAsync(ps->posY, posY, nb, cudaMemcpyHostToDevice, c->stream));
     for (int t = 0; t < 4; t++)
         if (props && props[t]) IFL_CUDA(cudaMemcpyAsync(ps->prop[t], props[t], nb, cudaMemcpyHostToDevice, c->stream));
+    // the slots past the uploaded set read as zero, like a fresh reference allocation (seedParticles may look
+    // at them)
+    const size_t tail = (size_t)(ps->capacity - count) * sizeof(double);
+    if (tail) {
+        IFL_CUDA(cudaMemsetAsync(ps->posX + count, 0, tail, c->stream));
+        IFL_CUDA(cudaMemsetAsync(ps->posY + count, 0, tail, c->stream));
+        for (int t = 0; t < 4; t++) IFL_CUDA(cudaMemsetAsync(ps->prop[t] + count, 0, tail, c->stream));
+    }
     IFL_CUDA(cudaStreamSynchronize(c->stream));
     ps->count = count;
     ps->binned = false;
     return IFL_OK;
 }
 
-int flip_get_particles(ifl_ctx *c, int *count, double *posX, double *posY, double *const *props) {
+int flip_get_particles(ifl_ctx *c, long long *count, double *posX, double *posY, double *const *props) {
     ParticleSet *ps = (ParticleSet *)c->particles;
     const size_t nb = (size_t)ps->count * sizeof(double);
     if (count) *count = ps->count;
@@ -334,7 +425,7 @@ int launch_grid_to_particles(ifl_ctx *c, double alpha) {
     const int fields[4] = {IFL_FIELD_D, IFL_FIELD_T, IFL_FIELD_U, IFL_FIELD_V};
     ProfScope scope(c, IFL_K_G2P);
     for (int t = 0; t < 4; t++) {
-        k_grid_to_particles<<<(ps->count + 255) / 256, 256, 0, c->stream>>>(c->fd[fields[t]], ps->prop[t], ps->posX,
+        k_grid_to_particles<<<(unsigned)((ps->count + 255) / 256), 256, 0, c->stream>>>(c->fd[fields[t]], ps->prop[t], ps->posX,
                                                                             ps->posY, ps->count, alpha);
         IFL_LAUNCHED(c);
     }
@@ -359,7 +450,7 @@ int launch_particles_advect(ifl_ctx *c, double timestep) {
     ParticleSet *ps = (ParticleSet *)c->particles;
     if (ps->count == 0) return IFL_OK;
     ProfScope scope(c, IFL_K_ADVECT);
-    k_particles_advect<<<(ps->count + 255) / 256, 256, 0, c->stream>>>(ps->posX, ps->posY, ps->count, c->fd[IFL_FIELD_U],
+    k_particles_advect<<<(unsigned)((ps->count + 255) / 256), 256, 0, c->stream>>>(ps->posX, ps->posY, ps->count, c->fd[IFL_FIELD_U],
                                                                        c->fd[IFL_FIELD_V], timestep, c->hx, c->W, c->H,
                                                                        c->bodies_d, c->n_bodies);
     IFL_LAUNCHED(c);

@@ -530,6 +530,7 @@ int ifl_extrapolate(ifl_ctx *c, int field) {
     TRY(need_solids(c, "ifl_extrapolate"));
     TRY(check_field(c, field));
     TRY(dist_barrier(c));
+    if (c->version >= 8) return flip_extrapolate(c, field); // + CELL_EMPTY cells, stack-ordered (v8:611-651)
     return launch_extrapolate(c, field);
 }
 
@@ -596,9 +597,46 @@ static int need_flip(ifl_ctx *c, const char *what) {
     return IFL_OK;
 }
 
-int ifl_particles_capacity(const ifl_ctx *c) { return (c && c->version >= 8) ? c->W * c->H * 12 : 0; }
+long long ifl_particles_capacity(const ifl_ctx *c) { return (c && c->version >= 8) ? flip_particle_capacity(c) : 0; }
+long long ifl_particles_count(const ifl_ctx *c) { return (c && c->version >= 8) ? flip_particle_count(c) : 0; }
 
-int ifl_particles_upload(ifl_ctx *c, int count, const double *px, const double *py, const double *pd, const double *pt,
+int ifl_particles_init(ifl_ctx *c, int avg_per_cell) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_init"));
+    return flip_particles_init(c, avg_per_cell);
+}
+
+int ifl_count_particles(ifl_ctx *c) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_count_particles"));
+    return flip_count_particles(c);
+}
+
+int ifl_prune_particles(ifl_ctx *c) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_prune_particles"));
+    return flip_prune_particles(c);
+}
+
+int ifl_seed_particles(ifl_ctx *c) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_seed_particles"));
+    return flip_seed_particles(c);
+}
+
+int ifl_particles_to_grid(ifl_ctx *c, long long *count) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_to_grid"));
+    return flip_particles_to_grid(c, count);
+}
+
+int ifl_particles_peek(ifl_ctx *c, int what, long long first, long long n, void *host) {
+    CHECK_CTX(c);
+    TRY(need_flip(c, "ifl_particles_peek"));
+    return flip_peek(c, what, first, n, host);
+}
+
+int ifl_particles_upload(ifl_ctx *c, long long count, const double *px, const double *py, const double *pd, const double *pt,
                          const double *pu, const double *pv) {
     CHECK_CTX(c);
     TRY(need_flip(c, "ifl_particles_upload"));
@@ -610,7 +648,7 @@ int ifl_particles_upload(ifl_ctx *c, int count, const double *px, const double *
     return flip_set_particles(c, count, px, py, props);
 }
 
-int ifl_particles_download(ifl_ctx *c, int *count, double *px, double *py, double *pd, double *pt, double *pu,
+int ifl_particles_download(ifl_ctx *c, long long *count, double *px, double *py, double *pd, double *pt, double *pu,
                            double *pv) {
     CHECK_CTX(c);
     TRY(need_flip(c, "ifl_particles_download"));
@@ -943,17 +981,48 @@ static int update_heat(ifl_ctx *c, double timestep, ifl_solve_info *infos) {
     for (int i = 0; i < 4; i++) TRY(ifl_flip(c, fields[i]));
     return IFL_OK;
 }
+// FluidSolver::update of chapter 8 (v8:1350-1413): particles -> grid, the chapter-7 solves between copy() and
+// diff(), grid -> particles, particle advection.  infos[0] = heat solve, infos[1] = pressure solve.
+static int update_flip(ifl_ctx *c, double timestep, ifl_solve_info *infos) {
+    const int fields[4] = {IFL_FIELD_D, IFL_FIELD_T, IFL_FIELD_U, IFL_FIELD_V};
+    const double flip_alpha = 0.001; // _flipAlpha v8:1296
+    ifl_solve_info local[2];
+    if (!infos) infos = local;
+    for (int i = 0; i < 4; i++) TRY(launch_fill_solid_fields(c, fields[i]));
+    TRY(flip_particles_to_grid(c, nullptr));
+    for (int i = 0; i < 4; i++) TRY(launch_copy(c, fields[i]));
+    // the inflow lives INSIDE update in this chapter (v8:1368)
+    TRY(ifl_add_inflow_t(c, 0.45, 0.2, 0.2, 0.05, 1.0, c->t_amb, 0.0, 0.0));
+    Arr &tsrc = c->fd[IFL_FIELD_T].src;
+    TRY(copy_own_rows(c, c->r, tsrc)); // v8:1370
+    TRY(launch_build_heat_matrix(c, timestep));
+    TRY(launch_mic0_factor(c));
+    TRY(pcg_project(c, 2000, &infos[0]));
+    TRY(copy_own_rows(c, tsrc, c->p)); // v8:1374
+    TRY(flip_extrapolate(c, IFL_FIELD_T));
+    TRY(launch_add_buoyancy(c, timestep));
+    TRY(launch_set_boundary_condition(c));
+    TRY(launch_build_rhs(c));
+    TRY(launch_compute_densities(c));
+    TRY(launch_build_matrix(c, timestep, c->rho_air));
+    TRY(launch_mic0_factor(c));
+    TRY(pcg_project(c, 2000, &infos[1]));
+    TRY(launch_apply_pressure(c, timestep, c->rho_air));
+    TRY(flip_extrapolate(c, IFL_FIELD_D));
+    TRY(flip_extrapolate(c, IFL_FIELD_U));
+    TRY(flip_extrapolate(c, IFL_FIELD_V));
+    TRY(launch_set_boundary_condition(c));
+    for (int i = 0; i < 4; i++) TRY(launch_diff(c, fields[i], flip_alpha, 0));
+    TRY(launch_grid_to_particles(c, flip_alpha));
+    for (int i = 0; i < 4; i++) TRY(launch_diff(c, fields[i], flip_alpha, 1));
+    return launch_particles_advect(c, timestep);
+}
 #undef B
 
 static int update_impl(ifl_ctx *c, double timestep, double density, ifl_solve_info *infos) {
     ifl_solve_info local;
     ifl_solve_info *info = infos ? infos : &local;
-    if (c->version >= 8) {
-        set_error("ifl_update: the chapter-8 step needs particle bookkeeping (seed/prune, v8:754-813) and the "
-                  "order-dependent empty-cell extrapolation (v8:611-651), which are not on the device yet; "
-                  "drive the stages individually");
-        return IFL_E_ARG;
-    }
+    if (c->version >= 8) return update_flip(c, timestep, infos);
     if (c->version >= 6) return update_heat(c, timestep, infos);
     if (c->version >= 4) return update_solids(c, timestep, density, info);
     // Row-slab multi-GPU: dist_barrier (a no-op on one GPU) sits wherever the next kernel reads

@@ -310,8 +310,18 @@ int launch_extrapolate(ifl_ctx *c, int field);
 // flip_kernels.cu (chapter 8)
 int flip_init(ifl_ctx *c);
 void flip_free(ifl_ctx *c);
-int flip_set_particles(ifl_ctx *c, int count, const double *posX, const double *posY, const double *const *props);
-int flip_get_particles(ifl_ctx *c, int *count, double *posX, double *posY, double *const *props);
+int flip_set_particles(ifl_ctx *c, long long count, const double *posX, const double *posY, const double *const *props);
+int flip_get_particles(ifl_ctx *c, long long *count, double *posX, double *posY, double *const *props);
+// flip_book.cu: particle bookkeeping (v8:735-813) and the chapter-8 extrapolation (v8:478-651)
+int flip_particles_init(ifl_ctx *c, int avg_per_cell);      // initParticles + gridToParticles(1.0) (ctors v8:877, 1306-1314)
+int flip_count_particles(ifl_ctx *c);                       // countParticles v8:754
+int flip_prune_particles(ifl_ctx *c);                       // pruneParticles v8:766
+int flip_seed_particles(ifl_ctx *c);                        // seedParticles  v8:789
+int flip_particles_to_grid(ifl_ctx *c, long long *count);   // particlesToGrid v8:916-927
+int flip_extrapolate(ifl_ctx *c, int field);                // FluidQuantity::extrapolate v8:611-651
+long long flip_particle_count(const ifl_ctx *c);
+long long flip_particle_capacity(const ifl_ctx *c);
+int flip_peek(ifl_ctx *c, int what, long long first, long long n, void *host); // test hook: raw slots incl. the stale tail
 int launch_from_particles(ifl_ctx *c, int field);
 int launch_grid_to_particles(ifl_ctx *c, double alpha);
 int launch_copy(ifl_ctx *c, int field);

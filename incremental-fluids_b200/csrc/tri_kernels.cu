@@ -316,37 +316,56 @@ __device__ void gatekeeper_warp(const TriParams &P, double *halo_s, uint64_t *fu
     Watch watch;
     mbar_wait(&full[0], 0, dead, P.scal); // operand block 0
     if (has_up && !hb) {
-        // LL messages in global memory: one L2 (NVLink) round trip serves 32 columns -- a poll per group of 8
-        // would not keep up with the producer (a round trip outlasts 8 steps) -- and groups are released as
-        // their messages turn up
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-            if (c0 + 32 > HRC) wait_counter(progress_addr, (unsigned)(c0 + 32 - HRC), dead, P.scal);
-            for (int b = c0 / BW; b <= (c0 + 31) / BW && b * BW < ncols; b++) // both operand blocks of this chunk
-                if (b > 0) mbar_wait(&full[b % NST], (unsigned)((b / NST) & 1), dead, P.scal);
-            const int c = c0 + lane;
-            bool have = false;
-            unsigned published = 0;
-            while (published < 32) {
-                if (!have) {
-                    double v;
-                    if (remote ? ll_load_sys(up_row + c, P.epoch, v) : ll_load(up_row + c, P.epoch, v)) {
-                        halo_s[c % HRC] = v;
-                        have = true;
-                        watch = Watch();
-                    } else if (watch.expired(dead)) {
-                        *dead = 1;
-                        P.scal->watchdog = 1;
-                        have = true;
+        // LL messages in global memory.  Lane l owns columns l, l + 32, l + 64, ... and walks them on its own,
+        // two polls in flight, so the L2 round trip (~0.4 us; a group of 8 columns arrives every ~0.5 us) is
+        // pipelined across columns instead of being paid once per batch.  (Measured with a batch of 32 columns
+        // polled to completion before the next: the first strip behind every L2 hand-off ran at 74 instead of
+        // 62 ns per step, 50 us per sweep, profiles/r02_tri_experiments.txt.)  The gate is the contiguous
+        // prefix of received columns, rounded down to whole groups.
+        int next_c = lane;         // this lane's first column not yet received
+        unsigned released = 0;     // columns released to the compute warp
+        int loaded_blocks = 1;     // operand blocks known to have landed
+        while (released < (unsigned)ncols) {
+            // ring slots are reused every HRC columns: stay behind the strip's own last row
+            const int limit = (int)lds_u32_volatile(progress_addr) + HRC;
+            double v0 = 0.0, v1 = 0.0;
+            bool ok0 = false, ok1 = false;
+            const int c0 = next_c, c1 = next_c + 32;
+            if (c0 < ncols && c0 < limit) ok0 = remote ? ll_load_sys(up_row + c0, P.epoch, v0) : ll_load(up_row + c0, P.epoch, v0);
+            if (c1 < ncols && c1 < limit) ok1 = remote ? ll_load_sys(up_row + c1, P.epoch, v1) : ll_load(up_row + c1, P.epoch, v1);
+            if (ok0) {
+                halo_s[c0 % HRC] = v0;
+                next_c = c1;
+                if (ok1) {
+                    halo_s[c1 % HRC] = v1;
+                    next_c = c1 + 32;
+                }
+            }
+            const unsigned prefix = __reduce_min_sync(0xffffffffu, (unsigned)imin(next_c, ncols));
+            const unsigned groups = prefix / HG * HG;
+            if (groups > released) {
+                __threadfence_block(); // halo_s values before the counter
+                __syncwarp();
+                // The compute warp may touch every column below the gate, so the gate never passes the operand
+                // blocks that have landed; it is published block by block -- a block further ahead only loads once
+                // the compute warp, fed by the gate published so far, has released the stage it needs.
+                while (released < groups) {
+                    const unsigned upto = umin(groups, (unsigned)(loaded_blocks * BW));
+                    if (upto > released) {
+                        if (lane == 0) sts_u32_volatile(gate_addr, upto);
+                        released = upto;
+                    }
+                    if (released < groups) {
+                        mbar_wait(&full[loaded_blocks % NST], (unsigned)((loaded_blocks / NST) & 1), dead, P.scal);
+                        loaded_blocks++;
+                        if (*dead) break;
                     }
                 }
-                const unsigned mask = __ballot_sync(0xffffffffu, have);
-                const unsigned lead = (mask == 0xffffffffu) ? 32u : (unsigned)(__ffs(~mask) - 1);
-                const unsigned groups = lead / HG * HG;
-                if (groups > published) {
-                    __threadfence_block(); // halo_s values before the counter
-                    if (lane == 0) sts_u32_volatile(gate_addr, (unsigned)c0 + groups);
-                    published = groups;
-                }
+                watch = Watch();
+            } else if (watch.expired(dead)) {
+                *dead = 1;
+                P.scal->watchdog = 1;
+                break;
             }
         }
         return;

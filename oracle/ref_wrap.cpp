@@ -57,6 +57,27 @@ static int ref_capture(const char *fmt, ...) {
 #define REF_CAT(a, b) REF_CAT2(a, b)
 #define REF_NS REF_CAT(ref_v, REF_VER)
 
+/* The reference reads memory it never initialised (`new double[]` without a fill: _dst, _z, _s, _precon,
+ * the particle arrays past _particleCount, ...).  At the shipped sizes glibc hands out
+ * fresh zero pages for those blocks; the harness pins that behaviour at every size by making every
+ * allocation of this library zero-filled (the library is built with hidden visibility, so these
+ * replacements serve only the code in it). */
+#include <new>
+void *operator new[](size_t n) {
+    void *p = calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void *operator new(size_t n) {
+    void *p = calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void operator delete[](void *p) noexcept { free(p); }
+void operator delete(void *p) noexcept { free(p); }
+void operator delete[](void *p, size_t) noexcept { free(p); }
+void operator delete(void *p, size_t) noexcept { free(p); }
+
 #define main ref_main
 #define class struct
 #define protected public /* SolidBody spells out "protected:" (v4:80) */
@@ -274,6 +295,9 @@ API int ref_call(void *p, const char *opname, const double *a, int na, double *o
         if (op == "qs.particleCount") { out[0] = qs->_particleCount; return 0; }
         if (op == "qs.setParticleCount") { qs->_particleCount = (int)a[0]; return 0; }
         if (op == "qs.particlesToGrid") { qs->particlesToGrid(); return 0; }
+        if (op == "qs.countParticles") { qs->countParticles(); return 0; }
+        if (op == "qs.pruneParticles") { qs->pruneParticles(); return 0; }
+        if (op == "qs.seedParticles") { qs->seedParticles(); return 0; }
         if (op == "qs.gridToParticles") { qs->gridToParticles(a[0]); return 0; }
         if (op == "qs.advect") { qs->advect(a[0], *s->_u, *s->_v); return 0; }
     }

@@ -24,12 +24,15 @@ REF_DIR = os.path.join(HERE, "_ref")
 # heap garbage instead, so the harness pins the "zero page" behaviour
 # (SURVEY.md 3.5 quirk 4).
 _UNINIT_SOLVER = ["r", "z", "s", "precon", "aDiag", "aPlusX", "aPlusY", "uDensity", "vDensity",
-                  "qs.weight", "qs.counts", "qs.posX", "qs.posY"]
+                  "qs.weight", "qs.counts"]
+# (the particle arrays are NOT in this list: the constructor has already filled them (initParticles, v8:877);
+# what lies past _particleCount is zero because ref_wrap.cpp zero-fills every allocation of the library)
 _UNINIT_QUANTITY = ["dst", "old", "normalX", "normalY", "body", "mask", "phi"]
 
 
 def available(version):
-    return os.path.exists(os.path.join(REF_DIR, "libref_v%d.so" % version))
+    """version: 1..8, or "8a8" for chapter 8 built with _AvgPerCell = 8 (BASELINE config 5)."""
+    return os.path.exists(os.path.join(REF_DIR, "libref_v%s.so" % version))
 
 
 def fnv64(arr):
@@ -46,8 +49,8 @@ def fnv64(arr):
 class Ref:
     """One reference FluidSolver instance of chapter `version` (1..8)."""
 
-    def __init__(self, version, w, h, params, bodies=(), fresh_copy=None, zero_uninit=True):
-        path = os.path.join(REF_DIR, "libref_v%d.so" % version)
+    def __init__(self, version, w, h, params, bodies=(), fresh_copy=None, zero_uninit=True, variant=""):
+        path = os.path.join(REF_DIR, "libref_v%d%s.so" % (version, variant))
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
         # v8's frand() keeps a function-static LCG seed (v8:38-46): a fresh

@@ -116,11 +116,12 @@ def test_4096_apply_pressure_and_advect(pair):
 # reference's cap of 600 with a residual that is still large, and 600 iterations of CG amplify ANY
 # rounding difference far beyond 1e-10.  The kernels are therefore pinned bit-exactly / at 1e-10 by a
 # short solve, and the whole capped steps are held against a MEASURED envelope: the same reference
-# code run twice, the second time with one rhs-feeding velocity sample moved by one ulp -- what the
-# reference itself does under the smallest possible perturbation at this size.  The twin is perturbed
-# ONCE; the device's reductions round differently in each of the 1200 dot products of a capped solve
-# (observed ratio ~14), hence the factor ENV_FACTOR.
-ENV_FACTOR = 64.0
+# code run again with 32 of the rhs-feeding velocity samples moved by one ulp -- what the reference
+# itself does under the smallest possible perturbation at this size.  The twin is perturbed ONCE, at the
+# start; the device's reductions round differently in each of the 1200 dot products of a capped solve, and
+# the non-converged iteration amplifies every one of them, hence the factor ENV_FACTOR on top.
+ENV_FACTOR = 32.0
+ENV_FLIPS = 32
 def ulp_flip(a, idx):
     b = a.view(np.int64)
     b[idx] += 1
@@ -147,7 +148,8 @@ def test_tall_grid_update_vs_oracle(ifl, port, w, h):
     assert rel_err(dev.get("p"), ora.p) <= REL
     # whole capped steps against the reference's own one-ulp envelope
     nz = np.flatnonzero(twin.src["v"])
-    ulp_flip(twin.src["v"], nz[len(nz) // 2])
+    for i in np.random.default_rng(1).choice(nz, ENV_FLIPS, replace=False):
+        ulp_flip(twin.src["v"], i)
     for step in range(2):
         sd = dev.update(0.005)
         so = ora.update(0.005)
@@ -156,7 +158,7 @@ def test_tall_grid_update_vs_oracle(ifl, port, w, h):
         for k in "duv":
             e = rel_err(dev.get(k + ".src"), ora.src[k])
             env = rel_err(twin.src[k], ora.src[k])
-            print("tall %dx%d step %d %s: device vs reference %.2e, reference vs reference+1ulp %.2e" % (w, h, step, k, e, env))
+            print("tall %dx%d step %d %s: device vs reference %.2e, reference vs reference+ulps %.2e" % (w, h, step, k, e, env))
             assert e <= max(REL, ENV_FACTOR * env), (step, k, e, env)
         for s in (dev, ora, twin):
             s.addInflow(*inflow)
