@@ -166,6 +166,8 @@ int ifl_fill(ifl_ctx *ctx, int buf, double value);
 int ifl_quantity_add_inflow(ifl_ctx *ctx, int field, double x0, double y0, double x1, double y1, double v);
 /* FluidQuantity::advect(timestep,u,v)  v2:170-183 (v1:125-138): src -> dst, reads u._src, v._src. */
 int ifl_advect(ifl_ctx *ctx, int field, double timestep);
+/* FluidSolver::maxTimestep()  1-matrixless/Fluid.cpp:310-328: 2*hx / max |(u, v)| at the cell centres, at most 1. */
+int ifl_max_timestep(ifl_ctx *ctx, double *result);
 /* FluidQuantity::flip()  v3:105-107. */
 int ifl_flip(ifl_ctx *ctx, int field);
 

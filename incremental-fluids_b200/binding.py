@@ -42,7 +42,7 @@ EXPORTS = [
     "ifl_destroy", "ifl_last_error", "ifl_launch_count", "ifl_stream", "ifl_sync",
     "ifl_profile", "ifl_profile_read", "ifl_debug_sweep_times",
     "ifl_buf_elems", "ifl_upload", "ifl_download", "ifl_fill",
-    "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip",
+    "ifl_quantity_add_inflow", "ifl_advect", "ifl_flip", "ifl_max_timestep",
     "ifl_set_bodies", "ifl_fill_solid_fields", "ifl_set_boundary_condition", "ifl_extrapolate",
     "ifl_aux_elems", "ifl_aux_download", "ifl_aux_upload",
     "ifl_set_fluid_params", "ifl_ambient_t", "ifl_build_heat_matrix", "ifl_add_buoyancy", "ifl_compute_densities",
@@ -106,6 +106,7 @@ def load_library():
     L.ifl_quantity_add_inflow.argtypes = [vp, ci, cd, cd, cd, cd, cd]
     L.ifl_advect.argtypes = [vp, ci, cd]
     L.ifl_flip.argtypes = [vp, ci]
+    L.ifl_max_timestep.argtypes = [vp, ctypes.POINTER(cd)]
     L.ifl_set_bodies.argtypes = [vp, vp, ci]
     L.ifl_fill_solid_fields.argtypes = [vp, ci]
     L.ifl_set_boundary_condition.argtypes = [vp]
@@ -262,6 +263,11 @@ class FluidSolver:
     def initParticles(self, avg_per_cell=4):
         """What the reference's two constructors do (v8:877, 1306-1314): initParticles + gridToParticles(1.0)."""
         self._chk(self.L.ifl_particles_init(self.ctx, avg_per_cell))
+
+    def maxTimestep(self):  # v1:310
+        out = ctypes.c_double()
+        self._chk(self.L.ifl_max_timestep(self.ctx, ctypes.byref(out)))
+        return out.value
 
     def particleCount(self):
         return int(self.L.ifl_particles_count(self.ctx))

@@ -151,6 +151,36 @@ static FieldView view(const Field &f) {
     return v;
 }
 
+// FluidSolver::maxTimestep v1:310-328: max over the cell centres of |(u, v)| (bilinear samples), as block
+// partials; the fold (a max: order-independent, exact) and 2*hx/max, min(.., 1.0) follow on the host side.
+__global__ void __launch_bounds__(256) k_max_velocity(FieldView u, FieldView v, int W, int H, int ry0, int ry1,
+                                                      double *__restrict__ partials) {
+    __shared__ double red[32];
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y0 = ry0 + blockIdx.y * 16, y1 = imin(imin(y0 + 16, ry1), H);
+    double m = 0.0;
+    if (x < W)
+        for (int y = y0; y < y1; y++) {
+            const double uu = lerp2(u, x + 0.5, y + 0.5);
+            const double vv = lerp2(v, x + 0.5, y + 0.5);
+            m = std_max(m, sqrt(uu * uu + vv * vv));
+        }
+    m = block_reduce<true>(m, red);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = m;
+}
+
+int launch_max_velocity(ifl_ctx *c) { // leaves the block partials in c->partials / c->n_partials
+    ProfScope ps_(c, IFL_K_ADVECT);
+    const Field &d = c->fd[IFL_FIELD_D];
+    const int ry0 = d.src.ry0, ry1 = d.src.ry1;
+    dim3 grid((c->W + 255) / 256, (ry1 - ry0 + 15) / 16); // as many partials as the PCG reductions: the buffer is sized for it
+    k_max_velocity<<<grid, 256, 0, c->stream>>>(view(c->fd[IFL_FIELD_U]), view(c->fd[IFL_FIELD_V]), c->W, c->H, ry0, ry1,
+                                               partials_next(c));
+    c->n_partials = (int)(grid.x * grid.y);
+    IFL_LAUNCHED(c);
+    return IFL_OK;
+}
+
 int launch_advect(ifl_ctx *c, int field, double timestep) {
     ProfScope ps_(c, IFL_K_ADVECT);
     Field &f = c->fd[field];

@@ -463,6 +463,24 @@ int ifl_advect(ifl_ctx *c, int field, double timestep) {
     return launch_advect(c, field, timestep);
 }
 
+int ifl_max_timestep(ifl_ctx *c, double *result) { // FluidSolver::maxTimestep v1:310-328
+    CHECK_CTX(c);
+    if (!result) return IFL_E_ARG;
+    if (c->world > 1) {
+        set_error("ifl_max_timestep is a one-GPU entry point");
+        return IFL_E_ARG;
+    }
+    TRY(launch_max_velocity(c));
+    double *dev_out = &c->scal->beta; // scratch slot; no solve is in flight
+    TRY(launch_finish_reduce(c, true, dev_out));
+    IFL_CUDA(cudaMemcpyAsync(c->result_h, dev_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IFL_CUDA(cudaStreamSynchronize(c->stream));
+    const double max_velocity = c->result_h[0];
+    const double dt = 2.0 * c->hx / max_velocity; // v1:324 (inf when the fluid is at rest)
+    *result = dt < 1.0 ? dt : 1.0;               // std::min(maxTimestep, 1.0)  v1:327
+    return IFL_OK;
+}
+
 int ifl_flip(ifl_ctx *c, int field) {
     CHECK_CTX(c);
     TRY(check_field(c, field));

@@ -12,6 +12,7 @@
 #include <stdio.h>
 
 #include "../../include/ifl_b200.h"
+#include "solid_geometry.cuh" // BodyDev + SolidBox / SolidSphere geometry (shared with the host drop-in header)
 
 namespace ifl {
 
@@ -50,14 +51,6 @@ struct Field { // one FluidQuantity (v3:41-49; solid-body members v5:288-313)
     int *solid_count;            // device counter for solid_list
 };
 
-// One SolidBody (v4:79-241) as plain data; sin/cos of theta are evaluated on the host
-// with libm so that rotate() (v4:58-62) is bit-identical to the reference.
-struct BodyDev {
-    int kind; // 0 SolidBox, 1 SolidSphere
-    int pad;
-    double posX, posY, scaleX, scaleY, theta, velX, velY, velTheta;
-    double cosT, sinT;
-};
 constexpr int MAX_BODIES = 256; // FluidQuantity::_body is uint8_t (v4:253)
 
 // Device-resident scalars of one PCG / Gauss-Seidel solve (no host round trips
@@ -124,6 +117,14 @@ struct ifl_ctx {
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     int tri_engine;                    // 1: triangular solves run on tri_kernels.cu (64-row strips)
+    // overlap of k_axpy2_norm with the forward sweep (pcg_kernels.cu): the streaming kernel runs on a side
+    // stream and counts finished blocks per 64-row band, the sweep's loader waits for its strip's band
+    int overlap_axpy;                  // 0 off, 1 plain streaming kernel first, 2 sweep first (experiment), 3 persistent streaming kernel
+    int sm_count;
+    cudaStream_t side_stream;
+    cudaEvent_t ev_alpha, ev_axpy;     // alpha is final (main -> side), r and |r| partials are final (side -> main)
+    unsigned *band_count;              // [strips of 64 rows] blocks of k_axpy2_norm finished so far (monotonic)
+    unsigned band_epoch;               // launches of the overlapped k_axpy2_norm so far
     int sweep_head_delay;              // SM cycles the head strip idles per macro-step (pace-setter, sweep_init)
     // row-slab multi-GPU: world == 1 unless the context came from ifl_create_dist
     int rank, world;
@@ -301,7 +302,7 @@ int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, boo
 int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve_info *info);
 // tri_kernels.cu: the two-rows-per-lane engine of the triangular solves (default; IFL_TRI=0 selects the
 // one-row engine of sweep_kernels.cu for A/B measurements)
-int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated);
+int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated, unsigned band_target = 0);
 int launch_tri_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 // solid_kernels.cu (chapters 4+)
 int launch_fill_solid_fields(ifl_ctx *c, int field);
@@ -337,5 +338,6 @@ int launch_add_buoyancy(ifl_ctx *c, double timestep);
 int launch_compute_densities(ifl_ctx *c);
 // advect_kernels.cu
 int launch_advect(ifl_ctx *c, int field, double timestep);
+int launch_max_velocity(ifl_ctx *c);
 
 } // namespace ifl

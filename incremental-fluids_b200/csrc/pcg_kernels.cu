@@ -128,9 +128,15 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
 }
 
 // p += alpha*s ; r += q*(-alpha) ; partial[block] = max|r|     v3:363-366
+// band_count (may be null): one counter per band of 64 rows; every block adds 1 to its band's counter after its
+// stores, so that the forward sweep -- launched concurrently on the main stream -- can start a strip as soon as
+// the rows it reads are final (blocks are 16 rows tall and never straddle a band).
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r, Arr q, const SolveScalars *sc,
-                                                             double *__restrict__ partials, CellMask mk) {
-    if (sc->done) return;
+                                                             double *__restrict__ partials, CellMask mk,
+                                                             unsigned *__restrict__ band_count) {
+    if (sc->done) { // the sweep does not wait either once the solve is over (it returns on the same flag)
+        return;
+    }
     __shared__ double red[32];
     const double alpha = sc->alpha;
     const double nalpha = -alpha;
@@ -159,8 +165,65 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
             st2(r.p + i, rv);
         }
     }
-    m = block_reduce<true>(m, red);
-    if (threadIdx.x == 0) partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = m;
+    m = block_reduce<true>(m, red); // (ends with a __syncthreads: every thread's stores precede the signal below)
+    if (threadIdx.x == 0) {
+        partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = m;
+        if (band_count) {
+            // every band counts 64 / VEC_ROWS slots per block column and launch; the last block row of a ragged grid
+            // (H not a multiple of 64) also signs for the slots that do not exist
+            const unsigned slots = (y0 + VEC_ROWS >= p.ry1) ? (unsigned)((64 - y0 % 64) / VEC_ROWS) : 1u;
+            __threadfence();
+            atomicAdd(&band_count[y0 / 64], slots);
+        }
+    }
+}
+
+// The same kernel as a PERSISTENT grid (a few blocks per SM, no shared memory to speak of) that walks the tiles of
+// k_axpy2_norm's grid band by band, top to bottom: it leaves room on every SM for the forward sweep's CTAs (which
+// need the SM's whole shared memory but only 224 threads), and finishes the bands in the order the sweep needs them.
+// Partials land in the slots of the plain kernel, so the folded norm is the same.
+__global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm_persistent(Arr p, Arr s, Arr r, Arr q, const SolveScalars *sc,
+                                                                        double *__restrict__ partials, CellMask mk,
+                                                                        unsigned *__restrict__ band_count, int gx, int gy) {
+    if (sc->done) return;
+    __shared__ double red[32];
+    const double alpha = sc->alpha;
+    const double nalpha = -alpha;
+    const int W = p.w, pitch = p.pitch;
+    for (int t = blockIdx.x; t < gx * gy; t += gridDim.x) {
+        const int bx = t % gx, by = t / gx;
+        const int x = bx * VEC_COLS + threadIdx.x * 2;
+        const int y0 = p.ry0 + by * VEC_ROWS;
+        const int y1 = imin(y0 + VEC_ROWS, p.ry1);
+        double m = 0.0;
+        if (x < W) {
+#pragma unroll 4
+            for (int y = y0; y < y1; y++) {
+                const size_t i = x + (size_t)y * pitch;
+                double2 pv = ld2(p.p + i), sv = ld2(s.p + i), rv = ld2(r.p + i), qv = ld2(q.p + i);
+                const bool f0 = mk.fluid(i), f1 = mk.fluid(i + 1);
+                if (f0) {
+                    pv.x = pv.x + sv.x * alpha;
+                    rv.x = rv.x + qv.x * nalpha;
+                    m = std_max(m, fabs(rv.x));
+                }
+                if (f1) {
+                    pv.y = pv.y + sv.y * alpha;
+                    rv.y = rv.y + qv.y * nalpha;
+                    m = std_max(m, fabs(rv.y));
+                }
+                st2(p.p + i, pv);
+                st2(r.p + i, rv);
+            }
+        }
+        m = block_reduce<true>(m, red);
+        if (threadIdx.x == 0) {
+            partials[(y0 / VEC_ROWS) * gx + bx] = m;
+            const unsigned slots = (y0 + VEC_ROWS >= p.ry1) ? (unsigned)((64 - y0 % 64) / VEC_ROWS) : 1u;
+            __threadfence();
+            atomicAdd(&band_count[y0 / 64], slots);
+        }
+    }
 }
 
 // dst = a + b*scale, scale either immediate or read from the device scalars (beta)
@@ -344,15 +407,42 @@ static int scalar_stage(ifl_ctx *c) {
 static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
-    {
-        ProfScope ps_(c, IFL_K_AXPY2_NORM);
-        k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, partials_next(c),
-                                                                    mask_of(c));
-        c->n_partials = vec_blocks(c->p);
+    if (c->overlap_axpy && c->tri_engine && !c->prof_on) {
+        // p += alpha s, r -= alpha q, |r|inf on the side stream, the forward sweep concurrently on the main stream:
+        // a strip starts when the 64-row band of r it reads is final (band counters).  The convergence test moves
+        // behind the sweep; a converged solve has then run one forward sweep it did not need (its result is unused).
+        IFL_CUDA(cudaEventRecord(c->ev_alpha, c->stream));
+        IFL_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_alpha, 0));
+        c->band_epoch++;
+        const dim3 g = vec_grid(c->p);
+        const unsigned target = c->band_epoch * g.x * (64 / VEC_ROWS);
+        double *parts = partials_next(c);
+        const int nparts = vec_blocks(c->p);
+        if (c->overlap_axpy == 2) // experiment: sweep first, plain streaming kernel second
+            IFL_TRY(launch_tri_forward(c, c->z, c->r, true, target));
+        if (c->overlap_axpy == 3)
+            k_axpy2_norm_persistent<<<c->sm_count * 4, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c),
+                                                                                        c->band_count, (int)g.x, (int)g.y);
+        else
+            k_axpy2_norm<<<g, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c), c->band_count);
         IFL_LAUNCHED(c);
+        IFL_CUDA(cudaEventRecord(c->ev_axpy, c->side_stream));
+        if (c->overlap_axpy != 2) IFL_TRY(launch_tri_forward(c, c->z, c->r, true, target));
+        IFL_CUDA(cudaStreamWaitEvent(c->stream, c->ev_axpy, 0));
+        c->partials = parts; // (the sweep launched no reduction in between)
+        c->n_partials = nparts;
+        IFL_TRY(scalar_stage<SC_CHECK>(c));
+    } else {
+        {
+            ProfScope ps_(c, IFL_K_AXPY2_NORM);
+            k_axpy2_norm<<<vec_grid(c->p), VEC_THREADS, 0, c->stream>>>(c->p, c->s, c->r, c->q, c->scal, partials_next(c),
+                                                                        mask_of(c), nullptr);
+            c->n_partials = vec_blocks(c->p);
+            IFL_LAUNCHED(c);
+        }
+        IFL_TRY(scalar_stage<SC_CHECK>(c));
+        IFL_TRY(launch_precon_forward(c, c->z, c->r, true));
     }
-    IFL_TRY(scalar_stage<SC_CHECK>(c));
-    IFL_TRY(launch_precon_forward(c, c->z, c->r, true));
     IFL_TRY(launch_precon_backward(c, c->z, c->r, true, true)); // partial z.r
     IFL_TRY(scalar_stage<SC_BETA>(c));
     {
@@ -369,6 +459,11 @@ int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
     // (the watchdog word is sticky: a factorisation sweep or a barrier that timed out BEFORE this
     // solve must still be seen by the first read-back below)
     IFL_CUDA(cudaMemsetAsync(c->scal, 0, offsetof(SolveScalars, watchdog), st));
+    // band counters of the overlapped k_axpy2_norm: launches that were gated off at the end of the previous solve
+    // never signalled, so every solve starts counting from zero (all of them have finished: the main stream waits
+    // for the side stream before every convergence test, and drains at the end of a solve)
+    IFL_CUDA(cudaMemsetAsync(c->band_count, 0, (size_t)((c->H + 63) / 64 + 1) * sizeof(unsigned), st));
+    c->band_epoch = 0;
     IFL_CUDA(cudaMemsetAsync((char *)c->p.p + c->p.own_begin(), 0, c->p.own_end() - c->p.own_begin(), st));
     IFL_TRY(dist_barrier(c, false)); // the upstream slab's last row of cy (factorisation) is final
     IFL_TRY(launch_precon_forward(c, c->z, c->r, false));

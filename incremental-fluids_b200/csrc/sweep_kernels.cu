@@ -886,6 +886,23 @@ int sweep_init(ifl_ctx *c) {
     // IFL_TRI=0 keeps them on this file's one-row engine for A/B measurements.
     c->tri_engine = 1;
     if (const char *e = getenv("IFL_TRI")) c->tri_engine = atoi(e) != 0;
+    // k_axpy2_norm overlapped with the forward sweep (pcg_kernels.cu, enqueue_iteration)
+    c->overlap_axpy = 3;
+    if (const char *e = getenv("IFL_OVERLAP_AXPY")) c->overlap_axpy = atoi(e);
+    {
+        cudaDeviceProp prop;
+        IFL_CUDA(cudaGetDeviceProperties(&prop, c->device));
+        c->sm_count = prop.multiProcessorCount;
+    }
+    IFL_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    IFL_CUDA(cudaEventCreateWithFlags(&c->ev_alpha, cudaEventDisableTiming));
+    IFL_CUDA(cudaEventCreateWithFlags(&c->ev_axpy, cudaEventDisableTiming));
+    {
+        const size_t nb = (size_t)((c->H + 63) / 64 + 1) * sizeof(unsigned);
+        IFL_CUDA(cudaMalloc(&c->band_count, nb));
+        IFL_CUDA(cudaMemset(c->band_count, 0, nb));
+        c->band_epoch = 0;
+    }
     c->map_cache = calloc(1, sizeof(MapCache));
     if (!c->map_cache) return IFL_E_NOMEM;
     c->epoch = 0;
@@ -896,6 +913,11 @@ void sweep_free(ifl_ctx *c) {
     if (c->handoff_base) dist_free_mem(c, c->handoff_base);
     c->handoff_base = nullptr;
     if (c->ticket) cudaFree(c->ticket);
+    if (c->band_count) cudaFree(c->band_count);
+    if (c->ev_alpha) cudaEventDestroy(c->ev_alpha);
+    if (c->ev_axpy) cudaEventDestroy(c->ev_axpy);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    c->band_count = nullptr;
     if (c->sweep_times_buf) cudaFree(c->sweep_times_buf);
     free(c->map_cache);
     c->handoff = nullptr;

@@ -93,6 +93,8 @@ struct TriParams {
     double *partials; // z.r per strip
     int cs;           // cluster size
     int head_delay;
+    const unsigned *band_count; // forward sweep overlapped with k_axpy2_norm: finished blocks per 64-row band (or null)
+    unsigned band_target;       // ... a strip may read its band of the rhs once the counter has reached this
     unsigned long long *times;
 };
 
@@ -237,16 +239,16 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
     // blocks of a lane in macro-step m: after its transition (bA = m - q), before (bA - 1), look-ahead of the
     // r == 0 lanes (bA + 1); blocks outside [0, nbx) are only touched by lanes outside the strip and alias
     // valid memory
-    auto bases = [&](int m) {
-        const int bA = m - q;
-        const int sA = imin(imax(bA, 0), nbx - 1) % NST;
-        const int sB = imin(imax(bA - 1, 0), nbx - 1) % NST;
-        const int sN = imin(imax(bA + 1, 0), nbx - 1) % NST;
+    auto bases_of = [&](int sA, int sB, int sN) {
         LaneBases lb;
         lb.A = row0 + (uint32_t)(sA * STAGE_BYTES) - (uint32_t)(G::DIR * r);
         lb.B = row0 + (uint32_t)(sB * STAGE_BYTES) + (uint32_t)(G::DIR * (BW - r));
         lb.N = row0 + (uint32_t)(sN * STAGE_BYTES) - (uint32_t)(G::DIR * BW);
         return lb;
+    };
+    auto bases = [&](int m) { // general form (first / last macro-steps)
+        const int bA = m - q;
+        return bases_of(imin(imax(bA, 0), nbx - 1) % NST, imin(imax(bA - 1, 0), nbx - 1) % NST, imin(imax(bA + 1, 0), nbx - 1) % NST);
     };
     Ops ops;
     // everything that does not depend on the upstream strip happens BEFORE the wait for its first
@@ -254,16 +256,25 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
     wait_counter<false>(gate_addr, (unsigned)imin(HG, ncols), dead, P.scal); // block 0 loaded, first hand-off group here
     fetch<BWD>(ops, pos<BWD>(bases(0), 0, r), halo0); // step 0: lane 0 at column 0, the others idle on valid memory
     const int nm = nbx + 2; // macro-steps: lane 31 finishes column ncols-1 at step ncols + 30
+    int sm = 0;             // m % NST, kept incrementally (the per-macro-step bookkeeping is paid every 16 steps)
     for (int m = 0; m < nm; m++) {
         if (!has_up && P.head_delay > 0) { // pace-setter, see sweep_init
             const long long t_ = clock64();
             while (clock64() - t_ < P.head_delay) {}
         }
-        const LaneBases lb = bases(m);
-        const uint32_t h_cur = halo0 + (uint32_t)(((BW * m) % HRC) * 8);
-        const uint32_t h_next = halo0 + (uint32_t)(((BW * (m + 1)) % HRC) * 8);
+        LaneBases lb;
+        if (m >= 2 && m < nbx - 1) { // no block index leaves [0, nbx): stages by rotation
+            int a = sm - q;
+            a += a < 0 ? NST : 0;
+            const int b = a == 0 ? NST - 1 : a - 1, n = a == NST - 1 ? 0 : a + 1;
+            lb = bases_of(a, b, n);
+        } else {
+            lb = bases(m);
+        }
+        const uint32_t h_cur = halo0 + (uint32_t)(((BW * m) & (HRC - 1)) * 8);
+        const uint32_t h_next = halo0 + (uint32_t)(((BW * (m + 1)) & (HRC - 1)) * 8);
         // groups completed by the last row at kk == 6 / 14 of this macro-step: 2m-4, 2m-3 (m >= 2)
-        const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 4) % NBELL]), bell14 = smem_u32(&bell[(2 * m + NBELL - 3) % NBELL]);
+        const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 4) & (NBELL - 1)]), bell14 = smem_u32(&bell[(2 * m + NBELL - 3) & (NBELL - 1)]);
         if (m < 2)
             macro_step<BWD, 1>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         else if (m >= nbx)
@@ -272,8 +283,10 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
             macro_step<BWD, 0>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         if (m >= 2 && !(TRI_EXP & 32)) { // lane 31 has left block m-2: hand it to the storer (and, through it, the loader;
             __syncwarp();               // the storer issues the proxy fence before the TMA may overwrite the stage)
-            if (lane == 0) mbar_arrive(&done[(m - 2) % NST]);
+            const int sd = sm >= 2 ? sm - 2 : sm - 2 + NST;
+            if (lane == 0) mbar_arrive(&done[sd]);
         }
+        sm = sm == NST - 1 ? 0 : sm + 1;
     }
 }
 
@@ -285,6 +298,23 @@ __device__ void loader_warp(const TriParams &P, unsigned char *smem, uint64_t *f
     const int nbx = P.nbx;
     const int ty = BWD ? (P.nby - 1 - sj) : sj; // memory strip of this CTA
     const int box_y = BWD ? ty * SR : ty * SR - 1;
+    if (!BWD && P.band_count) {
+        // the rhs rows of this strip are being written by k_axpy2_norm on another stream: wait until every block of
+        // the band has signalled (release: __threadfence + atomicAdd; acquire here), then order the TMA reads after it
+        Watch watch;
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.band_count + ty) : "memory");
+            if (v >= P.band_target || P.scal->done) break;
+            if (watch.expired(dead)) {
+                *dead = 1;
+                P.scal->watchdog = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
     for (int b = 0; b < nbx; b++) {
         const int st = b % NST;
         if (b >= NST) mbar_wait(&empty[st], (unsigned)(((b / NST) - 1) & 1), dead, P.scal);
@@ -618,7 +648,7 @@ __global__ void __launch_bounds__(224, 1) k_tri(const __grid_constant__ TriParam
 static const Arr &precon_operand(ifl_ctx *c) { return c->version >= 4 ? c->pe : c->precon; }
 
 template <bool BWD, bool DOT>
-static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdot, bool gated) {
+static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdot, bool gated, unsigned band_target = 0) {
     using namespace tri;
     TriParams P;
     memset(&P, 0, sizeof P);
@@ -657,6 +687,8 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
     P.gated = gated ? 1 : 0;
     P.head_delay = c->sweep_head_delay;
     P.times = c->sweep_times;
+    P.band_count = band_target ? c->band_count : nullptr;
+    P.band_target = band_target;
     if (DOT) {
         P.partials = partials_next(c);
         c->n_partials = 2 * P.nby; // one per storer warp
@@ -693,8 +725,8 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
     return IFL_OK;
 }
 
-int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
-    return launch_tri<false, false>(c, a, dst, nullptr, gated);
+int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated, unsigned band_target) {
+    return launch_tri<false, false>(c, a, dst, nullptr, gated, band_target);
 }
 
 int launch_tri_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {

@@ -10,18 +10,18 @@
 int main(int argc, char **argv) {
     const int size = argc > 1 ? atoi(argv[1]) : 128;
     const int frames = argc > 2 ? atoi(argv[2]) : 5;
-    const double density = 0.1, timestep = 0.005;
+    const double density = 0.1, timestep = IFL_CHAPTER == 8 ? 0.0025 : 0.005; // v8:1478
     unsigned char *image = new unsigned char[(size_t)size * size * 4 * 2];
     size_t image_bytes = (size_t)size * size * 4;
     (void)density;
 #if IFL_CHAPTER >= 6
     // 6-heat/Fluid.cpp:1062-1098 (7-variable-density: densitySoot 1.0, box and inflow of v7:1099/1112)
-    const double densityAir = 0.1, densitySoot = IFL_CHAPTER == 7 ? 1.0 : 0.1, diffusion = 0.01;
+    const double densityAir = 0.1, densitySoot = IFL_CHAPTER == 8 ? 0.25 : IFL_CHAPTER == 7 ? 1.0 : 0.1, diffusion = 0.01; // v8:1475
     const bool renderHeat = true;
     image_bytes *= 2;
     std::vector<SolidBody *> bodies;
-#if IFL_CHAPTER == 7
-    bodies.push_back(new SolidBox(0.5, 0.6, 0.7, 0.1, M_PI * 0.25, 0.0, 0.0, 0.0));
+#if IFL_CHAPTER >= 7
+    bodies.push_back(new SolidBox(0.5, 0.6, 0.7, 0.1, M_PI * 0.25, 0.0, 0.0, 0.0)); // v7:1099, v8:1484
 #else
     bodies.push_back(new SolidBox(0.3, 0.6, 0.1, 0.5, -M_PI * 0.05, 0.0, 0.0, 0.0));
 #endif
@@ -39,7 +39,9 @@ int main(int argc, char **argv) {
 #endif
     for (int f = 0; f < frames; f++) {
         for (int i = 0; i < (IFL_CHAPTER == 6 ? 10 : 4); i++) { // v6:1084 runs 10 updates per frame
-#if IFL_CHAPTER == 7
+#if IFL_CHAPTER == 8
+            // the inflow lives inside update() in this chapter (v8:1368)
+#elif IFL_CHAPTER == 7
             solver->addInflow(0.45, 0.2, 0.1, 0.05, 1.0, solver->ambientT(), 0.0, 0.0); // v7:1112
 #elif IFL_CHAPTER == 6
             solver->addInflow(0.35, 0.9, 0.1, 0.05, 1.0, solver->ambientT() + 300.0, 0.0, 0.0); // v6:1086

@@ -274,6 +274,15 @@ API int ref_call(void *p, const char *opname, const double *a, int na, double *o
         for (size_t i = 0; i < hd->bodies.size(); i++) hd->bodies[i]->update(a[0]);
         return 0;
     }
+    if (op == "bodyGeometry") { /* a = {index, x, y} -> out = {distance, normalX, normalY, closestX, closestY} (v4:116-118) */
+        const SolidBody *b = hd->bodies[(int)a[0]];
+        double x = a[1], y = a[2];
+        out[0] = b->distance(x, y);
+        b->distanceNormal(out[1], out[2], x, y);
+        b->closestSurfacePoint(x, y);
+        out[3] = x; out[4] = y;
+        return 0;
+    }
     if (op == "bodyState") { /* a[0] = index -> out[0..7] */
         SolidBody *b = hd->bodies[(int)a[0]];
         out[0] = b->_posX; out[1] = b->_posY; out[2] = b->_scaleX; out[3] = b->_scaleY;

@@ -60,5 +60,13 @@ def test_two_ranks_solids_heat_density(chapter, w, h, steps):
 
 
 @pytest.mark.skipif(_gpus() < 4, reason="needs >= 4 GPUs")
-def test_four_ranks(chapter=3):
-    run_ranks(4, 3, 256, 256, 2)
+@pytest.mark.parametrize("chapter,w,h,steps", [(3, 256, 256, 2), (5, 256, 320, 2), (7, 320, 256, 1)])
+def test_four_ranks(chapter, w, h, steps):
+    run_ranks(4, chapter, w, h, steps)
+
+
+@pytest.mark.skipif(_gpus() < 8, reason="needs 8 GPUs")
+@pytest.mark.parametrize("chapter,w,h,steps", [(3, 512, 512, 2), (3, 1024, 1100, 1), (5, 512, 576, 1)])
+def test_eight_ranks(chapter, w, h, steps):
+    """Eight slabs of 64-row strips (the last one ragged at 1100 / 576 rows): bit-identical to one GPU."""
+    run_ranks(8, chapter, w, h, steps, timeout=600)

@@ -76,3 +76,104 @@ def test_plume_main_chapter6_against_reference():
     # heat solves are well conditioned (equal counts); the pressure solve with a solid body sits at
     # the reference's own noise floor: counts within a few iterations
     assert all(abs(a - b) <= 4 for a, b in zip(got, want)), (got, want)
+
+
+def _run(exe_name, *args):
+    exe = os.path.join(HOST, exe_name)
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", HOST])
+    out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return out.stdout
+
+
+def _bits(x):
+    return "%016x" % int(np.float64(x).view(np.uint64))
+
+
+@pytest.mark.parametrize("chapter", [5, 8])
+def test_class_surface_against_reference(chapter):
+    """FluidQuantity::lerp/cerp/at/cell/volume, SolidBody::distance/distanceNormal/closestSurfacePoint (host-callable
+    virtuals), maxTimestep and ParticleQuantities through the drop-in header (host/surface_check.cpp), bit for bit
+    against the unmodified reference's own methods."""
+    import math
+    from oracle import refapi
+    if not refapi.available(chapter):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    size = 96
+    got = dict(l.split("=") for l in _run("surface_v%d" % chapter, size).strip().splitlines() if "=" in l and "[" in l or l.startswith(("d.", "max", "solid", "particles")))
+    bodies = [[0.0, 0.5, 0.6, 0.7, 0.1, math.pi * 0.25, 0.0, 0.0, 0.0], [1.0, 0.2, 0.3, 0.2, 0.2, 0.3, 0.0, 0.0, 0.0]]
+    params = [0.1] if chapter < 6 else [0.1, 0.25, 0.01]
+    ref = refapi.Ref(chapter, size, size, params, bodies)
+    pts = [(0.31, 0.42), (0.5, 0.61), (0.22, 0.33), (0.9, 0.1)]
+    for b in range(2):
+        for k, (x, y) in enumerate(pts):
+            a = np.asarray([float(b), x, y])
+            ref.lib.ref_call(ref.ptr, b"bodyGeometry", a.ctypes.data, 3, ref._out.ctypes.data)
+            d, nx, ny, cx, cy = [float(v) for v in ref._out[:5]]
+            for name, want in (("distance", d), ("normalX", nx), ("normalY", ny), ("closestX", cx), ("closestY", cy)):
+                assert got["%s[%d][%d]" % (name, b, k)] == _bits(want), (name, b, k)
+    if chapter >= 6:
+        ref.call("addInflow", 0.45, 0.2, 0.15, 0.03, 1.0, ref.call("ambientT"), 0.5, 3.0)
+    else:
+        ref.call("addInflow", 0.45, 0.2, 0.15, 0.03, 1.0, 0.5, 3.0)
+    hx = 1.0 / size
+    sx = [0.47 / hx, 0.52 / hx + 0.37, 0.58 / hx]
+    sy = [0.205 / hx, 0.21 / hx + 0.41, 0.22 / hx]
+    for k in range(3):
+        assert got["d.lerp[%d]" % k] == _bits(ref.call("d.lerp", sx[k], sy[k])), k
+        assert got["v.lerp[%d]" % k] == _bits(ref.call("v.lerp", sx[k], sy[k])), k
+        if chapter <= 7:
+            assert got["d.cerp[%d]" % k] == _bits(ref.call("d.cerp", sx[k], sy[k])), k
+    assert got["d.at"] == _bits(ref.buf("d.src")[int(sx[1]) + int(sy[1]) * size])
+    # maxTimestep (v1:310-328) restated on the reference's fields
+    u = ref.buf("u.src").reshape(size, size + 1)
+    v = ref.buf("v.src").reshape(size + 1, size)
+    uc = u[:, :-1] * (1.0 - 0.5) + u[:, 1:] * 0.5
+    uc = uc * (1.0 - 0.0) + np.vstack([uc[1:], uc[-1:]]) * 0.0  # y + 0.5 - oy(0.5) is integral: weight 0 on the next row
+    vc = v[:-1, :] * (1.0 - 0.5) + v[1:, :] * 0.5
+    vmax = float(np.sqrt(uc * uc + vc * vc).max())
+    assert got["maxTimestep"] == _bits(min(2.0 * hx / vmax, 1.0))
+    ref.call("d.fillSolidFields")
+    assert int(got["solid_cells"]) == int((ref.buf("d.cell") == 1).sum())
+    if chapter >= 8:
+        assert int(got["particles"]) == int(ref.call("qs.particleCount"))
+    ref.close()
+
+
+@pytest.mark.parametrize("chapter,inflow", [(2, (0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)), (4, (0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)),
+                                            (5, (0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)), (8, None)])
+def test_plume_main_other_chapters_against_reference(chapter, inflow):
+    """The reference's main() of chapters 2, 4, 5 and 8 through the drop-in header: the stdout lines carry the
+    unmodified reference's iteration counts (Gauss-Seidel: exactly; PCG with a solid body: at its noise floor) and,
+    for chapter 8, its particle counts exactly."""
+    import math
+    from oracle import refapi
+    if not refapi.available(chapter):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    size, frames = 64, 2
+    out = _run("plume_v%d" % chapter, size, frames)
+    got = [int(x) for x in re.findall(r"(?:after|of) (\d+) iterations", out)]
+    box = [[0.0, 0.5, 0.6, 0.7, 0.1, math.pi * 0.25, 0.0, 0.0, 0.0]]
+    params = [0.1] if chapter < 6 else [0.1, 0.25, 0.01]
+    ref = refapi.Ref(chapter, size, size, params, box if chapter >= 4 else ())
+    want, counts = [], []
+    ref.log()
+    for f in range(frames):
+        for _ in range(4):
+            if inflow:
+                ref.call("addInflow", *inflow)
+            ref.call("update", 0.0025 if chapter == 8 else 0.005)
+            log = ref.log()
+            want += [int(x) for x in re.findall(r"(?:after|of) (\d+) iterations", log)]
+            counts += [int(x) for x in re.findall(r"Particle count: (\d+)", log)]
+        if chapter >= 4:
+            ref.call("bodiesUpdate", 0.005)
+    ref.close()
+    assert len(got) == len(want) and len(got) >= 8, (got, want)
+    if chapter <= 2:
+        assert got == want
+    else:
+        assert all(abs(a - b) <= max(4, b // 16) for a, b in zip(got, want)), (got, want)
+    if chapter == 8:
+        assert [int(x) for x in re.findall(r"Particle count: (\d+)", out)] == counts
