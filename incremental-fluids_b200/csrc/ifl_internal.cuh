@@ -116,10 +116,10 @@ struct ifl_ctx {
     unsigned long long sweep_launches; // sweeps launched so far
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
-    int tri_engine;                    // 1: triangular solves run on tri_kernels.cu (64-row strips)
+    int tri_engine;                    // triangular solves: 2 stair_kernels.cu (default), 1 tri_kernels.cu, 0 the one-row engine
     // overlap of k_axpy2_norm with the forward sweep (pcg_kernels.cu): the streaming kernel runs on a side
     // stream and counts finished blocks per 64-row band, the sweep's loader waits for its strip's band
-    int overlap_axpy;                  // 0 off, 1 plain streaming kernel first, 2 sweep first (experiment), 3 persistent streaming kernel
+    int overlap_axpy;                  // 0 off, 1 plain streaming kernel, >= 2 persistent streaming kernel (default 3)
     int sm_count;
     cudaStream_t side_stream;
     cudaEvent_t ev_alpha, ev_axpy;     // alpha is final (main -> side), r and |r| partials are final (side -> main)
@@ -304,6 +304,9 @@ int gs_project(ifl_ctx *c, int limit, double timestep, double density, ifl_solve
 // one-row engine of sweep_kernels.cu for A/B measurements)
 int launch_tri_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated, unsigned band_target = 0);
 int launch_tri_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
+// stair_kernels.cu: the staircase engine (cell B one column behind cell A), same contract
+int launch_stair_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated, unsigned band_target = 0);
+int launch_stair_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated);
 // solid_kernels.cu (chapters 4+)
 int launch_fill_solid_fields(ifl_ctx *c, int field);
 int launch_set_boundary_condition(ifl_ctx *c);

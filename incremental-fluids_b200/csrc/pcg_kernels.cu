@@ -407,7 +407,11 @@ static int scalar_stage(ifl_ctx *c) {
 static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
-    if (c->overlap_axpy && c->tri_engine && !c->prof_on) {
+    // (only while every strip of the sweep is resident at once.  With more strips than SMs the overlapped pair is much
+    // slower than the serial one -- measured at 16384^2, 256 strips: 27.0 instead of 11.4 ms per iteration,
+    // profiles/r02_tri_experiments.txt section 8; not investigated further)
+    const bool strips_resident = (c->ry1 - c->ry0 + 63) / 64 <= (c->sm_count / 8) * 8 - 16;
+    if (c->overlap_axpy && c->tri_engine && !c->prof_on && strips_resident) {
         // p += alpha s, r -= alpha q, |r|inf on the side stream, the forward sweep concurrently on the main stream:
         // a strip starts when the 64-row band of r it reads is final (band counters).  The convergence test moves
         // behind the sweep; a converged solve has then run one forward sweep it did not need (its result is unused).
@@ -418,16 +422,18 @@ static int enqueue_iteration(ifl_ctx *c) {
         const unsigned target = c->band_epoch * g.x * (64 / VEC_ROWS);
         double *parts = partials_next(c);
         const int nparts = vec_blocks(c->p);
-        if (c->overlap_axpy == 2) // experiment: sweep first, plain streaming kernel second
-            IFL_TRY(launch_tri_forward(c, c->z, c->r, true, target));
-        if (c->overlap_axpy == 3)
+        // The streaming kernel is launched FIRST: it never waits for the sweep, so whichever of the two the
+        // hardware makes resident first, the pair cannot deadlock (the sweep launched first on a full GPU can:
+        // measured, profiles/r02_tri_experiments.txt).  Mode 3 (default): persistent form, 4 CTAs per SM walking
+        // the bands top to bottom, so the first strips' bands complete first (717 vs 757 vs 771 ms per 600 iterations).
+        if (c->overlap_axpy >= 2)
             k_axpy2_norm_persistent<<<c->sm_count * 4, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c),
                                                                                         c->band_count, (int)g.x, (int)g.y);
         else
             k_axpy2_norm<<<g, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c), c->band_count);
         IFL_LAUNCHED(c);
         IFL_CUDA(cudaEventRecord(c->ev_axpy, c->side_stream));
-        if (c->overlap_axpy != 2) IFL_TRY(launch_tri_forward(c, c->z, c->r, true, target));
+        IFL_TRY(c->tri_engine == 2 ? launch_stair_forward(c, c->z, c->r, true, target) : launch_tri_forward(c, c->z, c->r, true, target));
         IFL_CUDA(cudaStreamWaitEvent(c->stream, c->ev_axpy, 0));
         c->partials = parts; // (the sweep launched no reduction in between)
         c->n_partials = nparts;

@@ -76,6 +76,66 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity, volati
         }
     }
 }
+// Same, for the helper warps of the staircase engine: the try_wait carries a suspend-time hint, so a waiting warp
+// re-polls every ~100 us instead of every few hundred ns (it is still woken when the phase completes).  Measured:
+// two storer warps + loader waiting with the default limit cost the compute warp 5.6 cycles per step
+// (profiles/r02_tri_experiments.txt, section 7).
+__device__ __forceinline__ bool mbar_try_hint(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, unsigned parity, volatile int *dead, SolveScalars *scal) {
+    if (mbar_try_hint(bar, parity)) return;
+    if (*dead) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (!mbar_try_hint(bar, parity)) {
+        if (*dead) return;
+        if (globaltimer_ns() - t0 > WATCHDOG_NS) {
+            *dead = 1;
+            scal->watchdog = 1;
+            return;
+        }
+    }
+}
+// For waits that are off the critical path (ring slots with stages of slack): non-blocking test + nanosleep, so the
+// waiting warp issues nothing at all in between.
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, volatile int *dead, SolveScalars *scal) {
+    if (mbar_test(bar, parity)) return;
+    if (*dead) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        __nanosleep(128);
+        if (mbar_test(bar, parity)) return;
+        if (*dead) return;
+        if (globaltimer_ns() - t0 > WATCHDOG_NS) {
+            *dead = 1;
+            scal->watchdog = 1;
+            return;
+        }
+    }
+}
 // TMA: one 2-D box global -> shared, completion counted in bytes on an mbarrier.
 // Out-of-range rows (y = -1 for the first strip) are filled with zeros by the hardware.
 __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {

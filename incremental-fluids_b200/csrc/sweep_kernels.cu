@@ -885,7 +885,7 @@ int sweep_init(ifl_ctx *c) {
     // The triangular solves of the PCG loop run on the two-rows-per-lane engine (tri_kernels.cu);
     // IFL_TRI=0 keeps them on this file's one-row engine for A/B measurements.
     c->tri_engine = 1;
-    if (const char *e = getenv("IFL_TRI")) c->tri_engine = atoi(e) != 0;
+    if (const char *e = getenv("IFL_TRI")) c->tri_engine = atoi(e);
     // k_axpy2_norm overlapped with the forward sweep (pcg_kernels.cu, enqueue_iteration)
     c->overlap_axpy = 3;
     if (const char *e = getenv("IFL_OVERLAP_AXPY")) c->overlap_axpy = atoi(e);
@@ -1043,6 +1043,7 @@ static int solve_stages(ifl_ctx *c) {
 }
 
 int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) {
+    if (c->tri_engine == 2) return launch_stair_forward(c, dst, a, gated);
     if (c->tri_engine) return launch_tri_forward(c, dst, a, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);
@@ -1057,6 +1058,7 @@ int launch_precon_forward(ifl_ctx *c, const Arr &dst, const Arr &a, bool gated) 
 }
 
 int launch_precon_backward(ifl_ctx *c, const Arr &dst, const Arr &r_for_dot, bool with_dot, bool gated) {
+    if (c->tri_engine == 2) return launch_stair_backward(c, dst, r_for_dot, with_dot, gated);
     if (c->tri_engine) return launch_tri_backward(c, dst, r_for_dot, with_dot, gated);
     SweepParams P;
     memset(&P, 0, sizeof P);

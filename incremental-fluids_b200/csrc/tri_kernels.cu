@@ -152,7 +152,7 @@ __device__ __forceinline__ uint32_t pos(const LaneBases &lb, int j, int r) {
 // exactly when lane t is inside at step k).
 template <bool BWD, int EDGE>
 __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, uint32_t h_next, uint32_t bell6, uint32_t bell14,
-                                           int m, int lane, int r, Carry &cr, Ops &ops, uint32_t progress_addr,
+                                           uint32_t done_addr, int m, int lane, int r, Carry &cr, Ops &ops, uint32_t progress_addr,
                                            uint32_t gate_addr, int ncols, volatile int *dead, SolveScalars *scal) {
     typedef Geo<BWD> G;
     uint32_t p = pos<BWD>(lb, 0, r);
@@ -162,6 +162,14 @@ __device__ __forceinline__ void macro_step(const LaneBases &lb, uint32_t h_cur, 
         // gate (hand-off values received AND operand blocks loaded, in columns): read four steps early,
         // tested when lane 0 is about to fetch the first column of the next group
         if (((kk + 5) % HG) == 0 && EDGE != 2 && !(TRI_EXP & 16)) gate_seen = lds_u32_volatile(gate_addr);
+        // lane 31 left block m-3 at the end of macro-step m-1: hand it to the storer (and, through it, the loader; the
+        // storer issues the proxy fence before the TMA may overwrite the stage).  The last store into it was issued
+        // five steps (~600 cycles) ago by this same warp, so lane 0's arrive needs no warp-wide fence: a __syncwarp()
+        // + arrive at the macro-step boundary drains every load in flight (measured on the staircase engine: 5.6 cycles
+        // per step, profiles/r02_tri_experiments.txt section 7).
+        if (kk == 4 && !(TRI_EXP & 32)) {
+            if (lane == 0 && done_addr != 0) mbar_arrive_addr(done_addr);
+        }
         if (((kk + 1) % HG) == 0 && EDGE != 2 && !(TRI_EXP & 16)) {
             const unsigned need = (unsigned)imin(BW * m + kk + 1 + HG, ncols);
             if (gate_seen < need) wait_counter<false>(gate_addr, need, dead, scal);
@@ -275,18 +283,18 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
         const uint32_t h_next = halo0 + (uint32_t)(((BW * (m + 1)) & (HRC - 1)) * 8);
         // groups completed by the last row at kk == 6 / 14 of this macro-step: 2m-4, 2m-3 (m >= 2)
         const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 4) & (NBELL - 1)]), bell14 = smem_u32(&bell[(2 * m + NBELL - 3) & (NBELL - 1)]);
+        const uint32_t done_addr = m >= 3 ? smem_u32(&done[sm >= 3 ? sm - 3 : sm - 3 + NST]) : 0u; // block m-3, released at step 4
         if (m < 2)
-            macro_step<BWD, 1>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
+            macro_step<BWD, 1>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         else if (m >= nbx)
-            macro_step<BWD, 2>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
+            macro_step<BWD, 2>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         else
-            macro_step<BWD, 0>(lb, h_cur, h_next, bell6, bell14, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
-        if (m >= 2 && !(TRI_EXP & 32)) { // lane 31 has left block m-2: hand it to the storer (and, through it, the loader;
-            __syncwarp();               // the storer issues the proxy fence before the TMA may overwrite the stage)
-            const int sd = sm >= 2 ? sm - 2 : sm - 2 + NST;
-            if (lane == 0) mbar_arrive(&done[sd]);
-        }
+            macro_step<BWD, 0>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         sm = sm == NST - 1 ? 0 : sm + 1;
+    }
+    if (!(TRI_EXP & 32)) { // the last block (nbx-1 = nm-3)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[(nbx - 1) % NST]);
     }
 }
 

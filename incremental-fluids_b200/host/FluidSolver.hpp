@@ -270,6 +270,7 @@ public:
 
     // the solver's quantities and particle set as reference-style objects (views, see the header comment)
     FluidQuantity quantity(int field) {
+        syncBodies(); // the view's fillSolidFields / extrapolate / advect see the bodies as they are now (v4:612)
         const bool u = field == IFL_FIELD_U, v = field == IFL_FIELD_V;
         return FluidQuantity(_ctx, field, _w + (u ? 1 : 0), _h + (v ? 1 : 0), u ? 0.0 : 0.5, v ? 0.0 : 0.5); // v3:404-406
     }
