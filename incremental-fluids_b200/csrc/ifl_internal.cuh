@@ -116,6 +116,7 @@ struct ifl_ctx {
     unsigned long long sweep_launches; // sweeps launched so far
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
+    int tri_cluster16;                 // tri_kernels.cu may use clusters of 16 when all strips are resident (IFL_TRI_CLUSTER16)
     int tri_engine;                    // triangular solves: 2 stair_kernels.cu (default), 1 tri_kernels.cu, 0 the one-row engine
     // overlap of k_axpy2_norm with the forward sweep (pcg_kernels.cu): the streaming kernel runs on a side
     // stream and counts finished blocks per 64-row band, the sweep's loader waits for its strip's band

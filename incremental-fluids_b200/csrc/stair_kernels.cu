@@ -46,6 +46,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 // Timing experiments (profiles/microbench/step_s.cu builds one binary per value; never set in the product
 // build): bit 0 no gate checks, bit 1 no progress store / bell, bit 2 no lane-0 hand-off select, bit 3 no
@@ -336,7 +337,10 @@ __device__ void compute_warp(const Params &P, unsigned char *smem, double *halo_
     }
     const int nm = nbx + NG; // macro-steps: lane 31's cell B finishes column ncols-1 at step ncols + 62
     int sm = 0;              // m % NST, kept incrementally
-    for (int m = 0; m < nm; m++) {
+    // Three loops (lanes entering / steady state / lanes leaving) rather than one loop with a three-way branch: the
+    // steady-state loop then has a single back edge and no register shuffling where the variants join.
+    auto run = [&](int m, auto edge_tag) {
+        constexpr int EDGE = decltype(edge_tag)::value;
         if (!has_up && P.head_delay > 0) { // pace-setter, see sweep_init
             const long long t_ = clock64();
             while (clock64() - t_ < P.head_delay) {}
@@ -358,14 +362,13 @@ __device__ void compute_warp(const Params &P, unsigned char *smem, double *halo_
         // groups completed by the last row at kk == 6 / 14 of this macro-step: 2m-8, 2m-7 (m >= 4)
         const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 8) & (NBELL - 1)]), bell14 = smem_u32(&bell[(2 * m + NBELL - 7) & (NBELL - 1)]);
         const uint32_t done_addr = m >= 2 ? smem_u32(&done[sm >= 2 ? sm - 2 : sm - 2 + NST]) : 0u; // stage m-2, released at step 4
-        if (m < NG)
-            macro_step<BWD, 1>(la, lbb, h_cur, h_next, bell6, bell14, done_addr, m, lane, rA, s, progress_addr, gate_addr, ncols, vcols, dead, P.scal);
-        else if (m >= nbx)
-            macro_step<BWD, 2>(la, lbb, h_cur, h_next, bell6, bell14, done_addr, m, lane, rA, s, progress_addr, gate_addr, ncols, vcols, dead, P.scal);
-        else
-            macro_step<BWD, 0>(la, lbb, h_cur, h_next, bell6, bell14, done_addr, m, lane, rA, s, progress_addr, gate_addr, ncols, vcols, dead, P.scal);
+        macro_step<BWD, EDGE>(la, lbb, h_cur, h_next, bell6, bell14, done_addr, m, lane, rA, s, progress_addr, gate_addr, ncols, vcols, dead, P.scal);
         sm = sm == NST - 1 ? 0 : sm + 1;
-    }
+    };
+    int m = 0;
+    for (; m < imin(NG, nm); m++) run(m, std::integral_constant<int, 1>());
+    for (; m < nbx; m++) run(m, std::integral_constant<int, 0>());
+    for (; m < nm; m++) run(m, std::integral_constant<int, 2>());
     if (!(STAIR_EXP & 1024)) { // the last stage (ns-1 = nm-2)
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[(ns - 1) % NST]);

@@ -870,6 +870,11 @@ int sweep_init(ifl_ctx *c) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) c->sweep_cluster = v;
     }
+    // tri_kernels.cu goes to the non-portable cluster size 16 when every strip of the sweep is resident at once
+    // (4096^2: 4 clusters instead of 8, 440 instead of 453 us per sweep, 1.140 instead of 1.163 ms per PCG iteration;
+    // profiles/r02_tri_experiments.txt section 10).  IFL_TRI_CLUSTER16=0 keeps 8.
+    c->tri_cluster16 = 1;
+    if (const char *e = getenv("IFL_TRI_CLUSTER16")) c->tri_cluster16 = atoi(e) != 0;
     // Every strip with an upstream neighbour runs at the same pace (the hand-off checks make it ~3 %
     // slower than the head strip), so the lag a strip picks up while it starts -- cold instruction
     // cache, first TMA tiles, first hand-off -- is frozen for the whole sweep: a consumer that is not

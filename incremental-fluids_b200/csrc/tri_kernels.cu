@@ -50,6 +50,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 // Timing experiments (profiles/tri_experiments.sh builds one library per value; never set in the
 // product build; results are garbage, only strip 0's step time is of interest): bit 1 (2) no helper
@@ -265,7 +266,8 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
     fetch<BWD>(ops, pos<BWD>(bases(0), 0, r), halo0); // step 0: lane 0 at column 0, the others idle on valid memory
     const int nm = nbx + 2; // macro-steps: lane 31 finishes column ncols-1 at step ncols + 30
     int sm = 0;             // m % NST, kept incrementally (the per-macro-step bookkeeping is paid every 16 steps)
-    for (int m = 0; m < nm; m++) {
+    auto run = [&](int m, auto edge_tag) {
+        constexpr int EDGE = decltype(edge_tag)::value;
         if (!has_up && P.head_delay > 0) { // pace-setter, see sweep_init
             const long long t_ = clock64();
             while (clock64() - t_ < P.head_delay) {}
@@ -284,13 +286,20 @@ __device__ void compute_warp(const TriParams &P, unsigned char *smem, double *ha
         // groups completed by the last row at kk == 6 / 14 of this macro-step: 2m-4, 2m-3 (m >= 2)
         const uint32_t bell6 = smem_u32(&bell[(2 * m + NBELL - 4) & (NBELL - 1)]), bell14 = smem_u32(&bell[(2 * m + NBELL - 3) & (NBELL - 1)]);
         const uint32_t done_addr = m >= 3 ? smem_u32(&done[sm >= 3 ? sm - 3 : sm - 3 + NST]) : 0u; // block m-3, released at step 4
-        if (m < 2)
-            macro_step<BWD, 1>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
-        else if (m >= nbx)
-            macro_step<BWD, 2>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
-        else
-            macro_step<BWD, 0>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
+        macro_step<BWD, EDGE>(lb, h_cur, h_next, bell6, bell14, done_addr, m, lane, r, cr, ops, progress_addr, gate_addr, ncols, dead, P.scal);
         sm = sm == NST - 1 ? 0 : sm + 1;
+    };
+    // ONE loop with a three-way branch.  (Three loops -- entering / steady / leaving -- make the head strip 4 % faster,
+    // 111.6 instead of 116.8 cycles per step, and the sweep 5 % SLOWER, 475 instead of 453 us: the downstream strips
+    // then run into an empty gate more often, and every such stall costs more than the step it saved;
+    // profiles/r02_tri_experiments.txt section 9, A/B on one box.)
+    for (int m = 0; m < nm; m++) {
+        if (m < 2)
+            run(m, std::integral_constant<int, 1>());
+        else if (m >= nbx)
+            run(m, std::integral_constant<int, 2>());
+        else
+            run(m, std::integral_constant<int, 0>());
     }
     if (!(TRI_EXP & 32)) { // the last block (nbx-1 = nm-3)
         __syncwarp();
@@ -679,13 +688,43 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
         c->epoch++;
         P.epoch = 1;
     }
-    P.cs = c->sweep_cluster;
     {   // this rank's strips, in sweep order (slabs are whole 64-row strips, dist.cu)
         const int s0 = c->ry0 / SR, s1 = (c->ry1 + SR - 1) / SR;
         P.nloc = s1 - s0;
         P.sj_base = BWD ? P.nby - s1 : s0;
         P.handoff_down = reinterpret_cast<uint4 *>(c->handoff_down[BWD ? 1 : 0]);
     }
+    const size_t smem = (size_t)NST * STAGE_BYTES + (size_t)HRC * sizeof(double);
+    const bool masked = c->version >= 4;
+    static bool attr_set[IFL_MAX_DEVICES][2][2][2]; // function attributes are per device
+    static int max16[IFL_MAX_DEVICES][2][2][2];     // co-resident clusters of 16 (non-portable size), per kernel
+    auto kern = masked ? k_tri<BWD, DOT, true> : k_tri<BWD, DOT, false>;
+    if (!attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked]) {
+        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int n16 = 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t q;
+            memset(&q, 0, sizeof q);
+            q.gridDim = dim3(16 * 64);
+            q.blockDim = dim3(224);
+            q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 16;
+            qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&n16, kern, &q) != cudaSuccess) n16 = 0;
+        }
+        cudaGetLastError();
+        max16[c->device % IFL_MAX_DEVICES][BWD][DOT][masked] = n16;
+        attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked] = true;
+    }
+    // Clusters of 16 (one per GPC) halve the hand-offs that travel through L2 -- each costs ~3 us against 2.9 inside a
+    // cluster -- as long as every strip is resident at once; otherwise the portable size 8, which packs more strips.
+    P.cs = c->sweep_cluster;
+    if (c->tri_cluster16 && P.cs == 8 && (P.nloc + 15) / 16 <= max16[c->device % IFL_MAX_DEVICES][BWD][DOT][masked]) P.cs = 16;
     const int n_clusters = (P.nloc + P.cs - 1) / P.cs;
     P.ticket = c->ticket;
     P.ticket_base = c->sweep_tickets;
@@ -700,15 +739,6 @@ static int launch_tri(ifl_ctx *c, const Arr &rhs, const Arr &dst, const Arr *rdo
     if (DOT) {
         P.partials = partials_next(c);
         c->n_partials = 2 * P.nby; // one per storer warp
-    }
-    const size_t smem = (size_t)NST * STAGE_BYTES + (size_t)HRC * sizeof(double);
-    const bool masked = c->version >= 4;
-    static bool attr_set[IFL_MAX_DEVICES][2][2][2]; // function attributes are per device
-    auto kern = masked ? k_tri<BWD, DOT, true> : k_tri<BWD, DOT, false>;
-    if (!attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked]) {
-        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        IFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set[c->device % IFL_MAX_DEVICES][BWD][DOT][masked] = true;
     }
     ProfScope ps_(c, BWD ? IFL_K_PRECON_BWD : IFL_K_PRECON_FWD);
     cudaLaunchConfig_t cfg;
