@@ -184,13 +184,22 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm(Arr p, Arr s, Arr r,
 // Partials land in the slots of the plain kernel, so the folded norm is the same.
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm_persistent(Arr p, Arr s, Arr r, Arr q, const SolveScalars *sc,
                                                                         double *__restrict__ partials, CellMask mk,
-                                                                        unsigned *__restrict__ band_count, int gx, int gy) {
+                                                                        unsigned *__restrict__ band_count, int gx, int gy,
+                                                                        unsigned *__restrict__ ticket, unsigned ticket_base) {
     if (sc->done) return;
     __shared__ double red[32];
+    __shared__ int s_t;
     const double alpha = sc->alpha;
     const double nalpha = -alpha;
     const int W = p.w, pitch = p.pitch;
-    for (int t = blockIdx.x; t < gx * gy; t += gridDim.x) {
+    for (;;) {
+        // blocks are handed out in order by a ticket, not striped over the CTAs: the forward sweep's CTAs already hold
+        // many SMs when this kernel starts, and the CTAs of this grid that are not resident yet would otherwise keep a
+        // share of EVERY band back until the resident ones had finished all of theirs
+        if (threadIdx.x == 0) s_t = (int)(atomicAdd(ticket, 1u) - ticket_base);
+        __syncthreads();
+        const int t = s_t;
+        if (t >= gx * gy) break; // (every CTA draws exactly one ticket too many: the host advances the base by total + grid)
         const int bx = t % gx, by = t / gx;
         const int x = bx * VEC_COLS + threadIdx.x * 2;
         const int y0 = p.ry0 + by * VEC_ROWS;
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy2_norm_persistent(Arr p, Ar
                 st2(r.p + i, rv);
             }
         }
-        m = block_reduce<true>(m, red);
+        m = block_reduce<true>(m, red); // (its barriers also keep s_t from being overwritten before every thread read it)
         if (threadIdx.x == 0) {
             partials[(y0 / VEC_ROWS) * gx + bx] = m;
             const unsigned slots = (y0 + VEC_ROWS >= p.ry1) ? (unsigned)((64 - y0 % 64) / VEC_ROWS) : 1u;
@@ -407,10 +416,12 @@ static int scalar_stage(ifl_ctx *c) {
 static int enqueue_iteration(ifl_ctx *c) {
     IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
-    // (only while every strip of the sweep is resident at once.  With more strips than SMs the overlapped pair is much
-    // slower than the serial one -- measured at 16384^2, 256 strips: 27.0 instead of 11.4 ms per iteration,
-    // profiles/r02_tri_experiments.txt section 8; not investigated further)
-    const bool strips_resident = (c->ry1 - c->ry0 + 63) / 64 <= (c->sm_count / 8) * 8 - 16;
+    // Only while the sweep leaves at least half of the SMs free.  A sweep CTA takes its SM's whole shared-memory
+    // carve-out and the streaming kernel's CTAs do not become resident next to it, so the streaming kernel runs on the
+    // SMs the sweep does not use: 64 strips at 4096^2 leave 84 of 148 (the overlap hides most of the kernel), 128 strips
+    // at 8192^2 leave 20 and the pair is twice as slow as the serial order (7.26 against 3.36 ms per iteration; 16384^2:
+    // 27.0 against 11.4; profiles/r02_tri_experiments.txt section 11).  (>= 10: experiments, force.)
+    const bool strips_resident = (c->ry1 - c->ry0 + 63) / 64 <= c->sm_count / 2 || c->overlap_axpy >= 10;
     if (c->overlap_axpy && c->tri_engine && !c->prof_on && strips_resident) {
         // p += alpha s, r -= alpha q, |r|inf on the side stream, the forward sweep concurrently on the main stream:
         // a strip starts when the 64-row band of r it reads is final (band counters).  The convergence test moves
@@ -427,8 +438,10 @@ static int enqueue_iteration(ifl_ctx *c) {
         // measured, profiles/r02_tri_experiments.txt).  Mode 3 (default): persistent form, 4 CTAs per SM walking
         // the bands top to bottom, so the first strips' bands complete first (717 vs 757 vs 771 ms per 600 iterations).
         if (c->overlap_axpy >= 2)
-            k_axpy2_norm_persistent<<<c->sm_count * 4, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c),
-                                                                                        c->band_count, (int)g.x, (int)g.y);
+            k_axpy2_norm_persistent<<<c->sm_count * 4, VEC_THREADS, 0, c->side_stream>>>(
+                c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c), c->band_count, (int)g.x, (int)g.y,
+                c->band_count + (c->H + 63) / 64, // the spare counter behind the bands: block tickets (zeroed with them)
+                (c->band_epoch - 1) * (g.x * g.y + (unsigned)c->sm_count * 4));
         else
             k_axpy2_norm<<<g, VEC_THREADS, 0, c->side_stream>>>(c->p, c->s, c->r, c->q, c->scal, parts, mask_of(c), c->band_count);
         IFL_LAUNCHED(c);
