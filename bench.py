@@ -242,36 +242,77 @@ class CpuSampler:
         fields = wl["fields"]
         dt = wl["dt"]
         if self.use_ref:
-            s = self.s = refapi.Ref(v, self.w, self.h, wl["params"], wl["bodies"] if v >= 4 else ())
+            variant = "a8" if (v == 8 and wl.get("avg_per_cell") == 8 and refapi.available("8a8")) else ""  # _AvgPerCell = 8 build
+            s = self.s = refapi.Ref(v, self.w, self.h, wl["params"], wl["bodies"] if v >= 4 else (), variant=variant)
             call = s.call
             inflow = list(wl["inflow"]) if wl["inflow"] is not None else None
             if inflow and len(inflow) == 8 and inflow[5] is None:
                 inflow[5] = call("ambientT")
-            ops = {"inflow": (lambda: call("addInflow", *inflow)) if inflow else (lambda: None),
-                   "rhs": lambda: call("buildRhs"), "pressure": lambda: call("applyPressure", dt),
-                   "advect": (lambda: [call(k + ".advect", dt) for k in fields]) if v <= 7 else (lambda: call("qs.advect", dt))}
-            if v >= 3:
-                ops.update({"matrix": lambda: call("buildPressureMatrix", dt), "precon": lambda: call("buildPreconditioner"),
-                            "project": lambda n: call("project", n)})
-            else:
-                ops.update({"matrix": lambda: None, "precon": lambda: None, "project": lambda n: call("project", n, dt)})
-            if v >= 4:
-                pre = ops["rhs"]
-                ops["rhs"] = lambda: ([call(k + ".fillSolidFields") for k in fields], pre())
-            if v >= 7:
-                m = ops["matrix"]
-                ops["matrix"] = lambda: (call("computeDensities"), m())
+            # FluidSolver::update of the chapter, cut at the pressure solve (v3:433-447, v5:1012-1038, v7:1120-1166,
+            # v8:1350-1413): everything before it, the solve, everything after it
+            def before_rhs():
+                if v >= 4:
+                    for k in fields:
+                        call(k + ".fillSolidFields")
+                if v >= 8:
+                    call("qs.particlesToGrid")
+                    for k in fields:
+                        call(k + ".copy")
+                    call("addInflow", 0.45, 0.2, 0.2, 0.05, 1.0, call("ambientT"), 0.0, 0.0)  # v8:1362
+                if v >= 6:  # heat: r = T, implicit diffusion solve (a handful of iterations), T = p, buoyancy
+                    s.buf("r")[...] = s.buf("t.src")
+                    call("buildHeatDiffusionMatrix", dt)
+                    call("buildPreconditioner")
+                    call("project", 2000)
+                    s.buf("t.src")[...] = s.buf("p")
+                    call("t.extrapolate")
+                    call("addBuoyancy", dt)
+                if v >= 4:
+                    call("setBoundaryCondition")
+
+            def rhs():
+                call("buildRhs")
+
+            def matrix():
+                if v >= 7:
+                    call("computeDensities")
+                if v >= 3:
+                    call("buildPressureMatrix", dt)
+
+            def after_solve():
+                call("applyPressure", dt)
+                if v >= 4:
+                    for k in "duv":
+                        call(k + ".extrapolate")
+                    call("setBoundaryCondition")
+                if v >= 8:
+                    for k in fields:
+                        call(k + ".diff", 0.001)  # _flipAlpha, v8:1287
+                    call("qs.gridToParticles", 0.001)
+                    for k in fields:
+                        call(k + ".undiff", 0.001)
+                    call("qs.advect", dt)
+                else:
+                    for k in fields:
+                        call(k + ".advect", dt)
+                    for k in fields:
+                        call(k + ".flip")
+
+            ops = {"inflow": (lambda: call("addInflow", *inflow)) if inflow else (lambda: None), "before": before_rhs,
+                   "rhs": rhs, "matrix": matrix, "precon": (lambda: call("buildPreconditioner")) if v >= 3 else (lambda: None),
+                   "project": (lambda n: call("project", n)) if v >= 3 else (lambda n: call("project", n, dt)),
+                   "after": after_solve}
             self.kind = "reference"
         else:
             if v > 3:
                 raise SystemExit("bench.py: oracle/_ref is not built and the C port covers chapters 1-3 only")
             from oracle import portapi
             s = self.s = portapi.PortSolver(v, self.w, self.h, wl["params"][0])
-            ops = {"inflow": lambda: s.addInflow(*wl["inflow"]), "rhs": s.buildRhs,
+            ops = {"inflow": lambda: s.addInflow(*wl["inflow"]), "before": lambda: None, "rhs": s.buildRhs,
                    "matrix": (lambda: s.buildPressureMatrix(dt)) if v >= 3 else (lambda: None),
                    "precon": s.buildPreconditioner if v >= 3 else (lambda: None),
                    "project": (lambda n: s.project(n)) if v >= 3 else (lambda n: s.project(n, dt)),
-                   "pressure": lambda: s.applyPressure(dt), "advect": lambda: [s.advect(k, dt) for k in "duv"]}
+                   "after": lambda: (s.applyPressure(dt), [s.advect(k, dt) for k in "duv"], [s.flip(k) for k in "duv"])}
             self.kind = "port"
         self.ops = ops
         self.t = {}
@@ -285,14 +326,14 @@ class CpuSampler:
     def setup(self):
         o = self.ops
         o["inflow"]()
+        self._timed("before", o["before"])
         self._timed("rhs", o["rhs"])
         self._timed("matrix", o["matrix"])
         self._timed("precon", o["precon"])
         self._timed("project0", o["project"], 0)  # prologue only (one applyPreconditioner, norm, dot)
-        self._timed("pressure", o["pressure"])
-        self._timed("advect", o["advect"])
+        self._timed("after", o["after"])
         t = self.t
-        self.fixed = t["rhs"] + t["matrix"] + t["precon"] + t["project0"] + t["pressure"] + t["advect"]
+        self.fixed = t["before"] + t["rhs"] + t["matrix"] + t["precon"] + t["project0"] + t["after"]
 
     def sample(self, k):
         """k more iterations of the solve from a fresh right-hand side; returns seconds per iteration."""
@@ -310,12 +351,12 @@ class CpuSampler:
         what = "PCG iterations" if self.v >= 3 else "Gauss-Seidel sweeps"
         n = sum(k for k, _ in self.iter_samples)
         mean = sum(k * p for k, p in self.iter_samples) / max(n, 1)
-        d = ("%s CPU code of chapter %d, 1 thread, %dx%d: assembly+prologue+applyPressure+advection timed in full once (%.2f s), "
-             "%d %s timed in %d sample(s) (%.3f s each on average), extrapolated to the %d of the device step"
+        d = ("%s CPU code of chapter %d, 1 thread, %dx%d: everything of update() but the pressure solve's iterations timed in full once (%.2f s), "
+             "%d %s timed in %d sample(s) (%.4f s each on average), extrapolated to the %d of the device step"
              % ("unmodified reference (oracle/_ref)" if self.use_ref else "C port of the reference (oracle/ifl_oracle.c)",
                 self.v, self.w, self.h, self.fixed, n, what, len(self.iter_samples), mean, full_iters))
         if self.v >= 6:
-            d += " (pressure solve only: the heat solve's handful of iterations and the particle transfers are not sampled)"
+            d += " (the heat solve and, in chapter 8, the particle transfers are inside the part timed in full)"
         if self.cell_scale != 1.0:
             d += "; scaled by %.2f (cells of the %dx%d workload / cells of the sample)" % (self.cell_scale, self.wl["size"], self.wl["size"])
         return d

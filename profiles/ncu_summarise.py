@@ -32,7 +32,7 @@ WANT = {
 }
 # algorithmic bytes per cell of the kernels that have one; the grid is given per report
 ALG = {"k_tri<0": 40, "k_tri<1": 48, "k_matvec": 40, "k_axpy2_norm": 48, "k_scaled_add": 24, "k_advect": 80.0 / 3,
-       "k_sweep<2": 32, "k_sweep<4": 32, "k_sweep<3": 24}
+       "k_sweep<2": 32, "k_sweep<4": 32, "k_sweep<3": 24, "k_build_rhs": 24, "k_build_matrix": 24, "k_apply_pressure": 24}
 CELLS = {"gs_sweep": 2048 * 2048, "p2g": 1024 * 1024, "g2p": 1024 * 1024, "padvect": 1024 * 1024}
 
 
@@ -85,7 +85,8 @@ lines = ["# ncu --set full, one launch per kernel class (round 2)", "",
 for r in rows:
     k = r["kernel"]
     short = re.sub(r"\(.*", "", k)
-    short = re.sub(r"ifl::(tri::)?", "", short)
+    short = re.sub(r"^void ", "", short)
+    short = re.sub(r"ifl::((tri|stair)::)?", "", short)
     cells = CELLS.get(r["report"], 4096 * 4096)
     alg = None
     for pat, b in ALG.items():
