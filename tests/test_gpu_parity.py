@@ -350,3 +350,55 @@ def test_update_edge_sizes(ifl, port, version, w, h):
         err = float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
         assert err <= 1e-10, (k, err)  # PCG results: <= 1e-10 relative (north star)
     dev.close()
+
+
+# ---- every sweep engine and cluster size does the same arithmetic ---------------------------------
+# The product runs the two-row engine in clusters of 16 / 8; the one-row engine (IFL_TRI=0), the staircase
+# engine (IFL_TRI=2), plain clusters of 8 and the serial order of k_axpy2_norm and the
+# forward sweep (IFL_OVERLAP_AXPY=0) are alternatives selected when a solver is created.
+ENGINE_ENVS = [{"IFL_TRI": "0"}, {"IFL_TRI": "2"}, {"IFL_TRI": "2", "IFL_OVERLAP_AXPY": "0"}, {"IFL_TRI_CLUSTER16": "0"},
+               {"IFL_OVERLAP_AXPY": "0"}, {"IFL_OVERLAP_AXPY": "1"}, {"IFL_SWEEP_CLUSTER": "1"}]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", ENGINE_ENVS, ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+@pytest.mark.parametrize("w,h", [(257, 130), (64, 700), (1024, 1024)])
+def test_engine_variants_bit_exact(ifl, port, monkeypatch, env, w, h):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dev, ora = make_pair(ifl, port, 3, w, h, seed=11)
+    for s in (dev, ora):
+        s.buildRhs(); s.buildPressureMatrix(0.005); s.buildPreconditioner()
+    assert_bits(dev.get("precon"), ora.precon, "buildPreconditioner")
+    dev.applyPreconditioner("z", "r"); ora.applyPreconditioner(ora.z, ora.r)
+    assert_bits(dev.get("z"), ora.z, "applyPreconditioner")
+    sd, so = dev.project(40), ora.project(40)
+    assert sd[:2] == so[:2], (sd, so)
+    assert rel_err(dev.get("p"), ora.p) <= REL
+    dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"IFL_TRI": "2"}, {"IFL_TRI": "0"}], ids=["staircase", "one-row"])
+def test_engine_variants_with_solids(ifl, monkeypatch, env):
+    """Masked form (v5:746-780) of the alternative engines against the unmodified reference."""
+    from oracle import refapi
+    import math
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    w, h = 200, 136
+    bodies = [ifl.SolidBox(0.5, 0.6, 0.7, 0.1, math.pi * 0.25, 0.0, 0.0, 0.0), ifl.SolidSphere(0.2, 0.3, 0.2, 0.0, 0.0, 0.0, 0.0)]
+    dev = ifl.FluidSolver(w, h, 0.1, version=5, bodies=bodies)
+    ref = refapi.Ref(5, w, h, [0.1], [b.as_row() for b in bodies])
+    inflow = (0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)
+    dev.addInflow(*inflow); ref.call("addInflow", *inflow)
+    for q in "duv":
+        dev.fillSolidFields(q); ref.call(q + ".fillSolidFields")
+    dev.setBoundaryCondition(); ref.call("setBoundaryCondition")
+    dev.buildRhs(); ref.call("buildRhs")
+    dev.buildPressureMatrix(0.005); ref.call("buildPressureMatrix", 0.005)
+    dev.buildPreconditioner(); ref.call("buildPreconditioner")
+    assert_bits(dev.get("precon"), ref.buf("precon"), "precon")
+    dev.applyPreconditioner("z", "r"); ref.call("applyPreconditioner", 2, 0)
+    assert_bits(dev.get("z"), ref.buf("z"), "applyPreconditioner (masked)")
+    dev.close(); ref.close()
