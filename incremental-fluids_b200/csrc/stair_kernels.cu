@@ -10,17 +10,21 @@
 //   floating-point operations on the same operands as the raster loop: results are bit-identical.
 //
 // A sweep is a wave that has to cross W + H cells, and every cell is a mul-sub-sub-mul chain of
-// FP64 operations (~12 cycles each) that cannot be reassociated.  Its duration is
+// FP64 operations (8.4 cycles each) that cannot be reassociated.  Its duration is
 //     (W + strips * (skew + hand-off)) * T_step.
-// The first two-row engine (tri_kernels.cu, kept for reference measurements: IFL_TRI=1) gave a lane two
-// vertically adjacent rows in the SAME column: cell B waited for cell A of the same step, so a step was
-// shuffle + 6 dependent FP64 operations = 98 cycles of pure latency (121 measured), 31 steps of skew per
-// 64-row strip.  Here cell B runs ONE COLUMN BEHIND cell A of its own lane: B takes A's value of the
-// previous step from a register, A takes the B of the lane above (previous step) by shuffle, and the two
-// chains of a step are independent.  The loop-carried cycle is B -> shuffle -> A -> B over two steps
-// (~49 cycles per step) or a row's own mul-sub-sub-mul (~48): half the old step.  The price is a skew of
-// two columns per lane, 63 steps per 64-row strip -- W + H steps in all, the length of the dependency
-// chain itself.
+// STATUS: bit-exact and selectable (IFL_TRI=2), NOT the default.  Measured at 4096^2 it ties with the two-row
+// engine of tri_kernels.cu (479-502 us per solve against 440-465): the step is shorter, 92-98 cycles against
+// 117-126, but the strip skew doubles.  DESIGN.md section 4 item 10 and profiles/r02_tri_experiments.txt
+// section 8 have the numbers and the breakdown of the step; the file stays because it is the better engine for
+// wide, short slabs (W >> H, e.g. many GPUs) and because its staging scheme is what a faster step would need.
+//
+// The two-row engine gives a lane two vertically adjacent rows in the SAME column: cell B waits for cell A of
+// the same step, so the loop-carried chain of a step is shuffle + 6 dependent FP64 operations (~65 cycles),
+// with 31 steps of skew per 64-row strip.  Here cell B runs ONE COLUMN BEHIND cell A of its own lane: B takes
+// A's value of the previous step from a register, A takes the B of the lane above (previous step) by shuffle,
+// and the two chains of a step are independent.  The loop-carried cycle is B -> shuffle -> A -> B over two
+// steps (~40 cycles per step) or a row's own mul-sub-sub-mul (34).  The price is a skew of two columns per
+// lane, 63 steps per 64-row strip -- W + H steps in all, the length of the dependency chain itself.
 //
 // Geometry
 //   * strip = 64 rows, one CTA (1 per SM).  Lane t = 8g + u owns rows 2t, 2t+1 of the strip (forward; the

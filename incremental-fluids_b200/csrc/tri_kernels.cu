@@ -17,7 +17,8 @@
 // the lane above by shuffle, as before, and cell B (lower row) takes A straight from a register.
 // A step is longer (one more mul-sub-mul chain) but a strip is 64 rows tall: half the strips, half
 // the hand-offs, half the skew steps, and the per-step overheads (hand-off polling, ring barriers,
-// address selects) are paid once for two rows.
+// address selects) are paid once for two rows.  Measured at 4096^2: T = 117 cycles, 48 steps (2.85 us)
+// of lag per strip, 440 us per solve.
 //
 // Geometry
 //   * strip = 64 rows, one CTA (1 per SM); lane t owns tile rows 1+2t, 2+2t (forward; tile row 0 is
@@ -25,8 +26,11 @@
 //     runs one column behind lane t-1: the warp is an anti-diagonal, 31 columns long.
 //   * operands are staged by TMA in blocks of 16 columns x 65 rows (one box per operand per block:
 //     rhs/z, cx, cy, precon), 6-stage ring.  Lanes 0..15 work in blocks m-1 and m, lanes 16..31 in
-//     m-2 and m-1; a block is released when lane 31 has left it.  Rows are dense (128 bytes), lane t
+//     m-2 and m-1; a block is released (lane 0 arrives on done[] from inside the step stream, five steps
+//     after lane 31 has left it -- no warp-wide fence).  Rows are dense (128 bytes), lane t
 //     reads column (k - t) mod 16: the 16 lanes of a half-warp hit 16 different 8-byte bank slots.
+//   * clusters of 16 CTAs (non-portable size) when every strip is resident at once, else of 8: inside a
+//     cluster the hand-off goes through distributed shared memory, between clusters through L2.
 //   * warps: 0 compute, 1 TMA loader, 2 storer (drains z, folds z.r reading r straight from global
 //     memory -- it does not depend on the sweep, so its loads are issued before the wait), 3 publisher,
 //     5 gatekeeper (strip-to-strip hand-off + TMA arrival -> one "gate" counter for the compute warp).
