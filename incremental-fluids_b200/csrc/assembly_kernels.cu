@@ -406,6 +406,9 @@ int launch_build_matrix(ifl_ctx *c, double timestep, double density) {
                                                                          c->fd[IFL_FIELD_V], scale, c->version >= 5);
     else
         k_build_matrix<<<grid_rows(c->aDiag), 256, 0, c->stream>>>(c->aDiag, c->aPlusX, c->aPlusY, scale);
+    // chapter 3: the matrix is a function of position and `scale` alone; k_matvec may evaluate it instead of reading it
+    c->matrix_uniform = (c->version == 3 && c->matvec_uniform_allowed) ? 1 : 0;
+    c->matrix_scale = scale;
     IFL_LAUNCHED(c);
     return IFL_OK;
 }

@@ -396,6 +396,7 @@ int ifl_upload(ifl_ctx *c, int buf, const double *host) {
         set_error("ifl_upload: bad buffer id %d", buf);
         return IFL_E_ARG;
     }
+    if (buf == IFL_BUF_ADIAG || buf == IFL_BUF_APLUSX || buf == IFL_BUF_APLUSY) c->matrix_uniform = 0; // the caller's own matrix
     // several ranks: collective; every rank passes the whole dense array and copies its own rows
     if (a->ry1 > a->ry0)
         IFL_CUDA(cudaMemcpy2DAsync(a->p + (size_t)a->ry0 * a->pitch, (size_t)a->pitch * 8, host + (size_t)a->ry0 * a->w,
@@ -1122,6 +1123,7 @@ int ifl_upload_slab(ifl_ctx *c, int buf, const double *host) {
         set_error("ifl_upload_slab: bad buffer id %d", buf);
         return IFL_E_ARG;
     }
+    if (buf == IFL_BUF_ADIAG || buf == IFL_BUF_APLUSX || buf == IFL_BUF_APLUSY) c->matrix_uniform = 0; // the caller's own matrix
     IFL_CUDA(cudaMemcpy2DAsync(a->p + (size_t)a->ry0 * a->pitch, (size_t)a->pitch * 8, host, (size_t)a->w * 8,
                                (size_t)a->w * 8, a->ry1 - a->ry0, cudaMemcpyHostToDevice, c->stream));
     IFL_CUDA(cudaStreamSynchronize(c->stream));

@@ -115,6 +115,9 @@ struct ifl_ctx {
     int n_strips;
     unsigned long long sweep_launches; // sweeps launched so far
     unsigned long long sweep_tickets;  // cluster tickets handed out by all previous sweeps
+    int matrix_uniform;                // chapter 3: the stored matrix is the one buildPressureMatrix wrote (k_matvec may evaluate it)
+    int matvec_uniform_allowed;        // IFL_MATVEC_UNIFORM=0 turns that off
+    double matrix_scale;               // its `scale` (v3:223)
     int sweep_cluster;                 // thread-block cluster size of the sweep kernels
     int tri_cluster16;                 // tri_kernels.cu may use clusters of 16 when all strips are resident (IFL_TRI_CLUSTER16)
     int tri_engine;                    // triangular solves: 2 stair_kernels.cu (default), 1 tri_kernels.cu, 0 the one-row engine

@@ -48,12 +48,22 @@ struct CellMask {
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
+// Chapter 3's matrix (v3:222-244) is a pure function of the cell's position: every existing neighbour contributes
+// `scale` to the diagonal -- equal addends, so the sum depends on their NUMBER only: d[n] = ((0 + s) + s) ... -- and
+// -scale to aPlusX / aPlusY.  UNIFORM evaluates those values in registers instead of reading 24 bytes per cell; the
+// products and their order are the ones of the stored matrix (which buildPressureMatrix still writes: the factorisation
+// and every accessor read it).  Off as soon as the caller uploads a matrix of their own.
+struct UniformMatrix {
+    double d[5];   // diagonal for 0..4 neighbours
+    double off;    // -scale
+};
+
 // dst = A*b (5-point stencil in the reference's summation order: diag, left, up,
 // right, down); optionally partial[block] = sum(dst*b) over the block's cells.
-template <bool WITH_DOT>
+template <bool WITH_DOT, bool UNIFORM>
 __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDiag, Arr aPlusX, Arr aPlusY,
                                                          double *__restrict__ partials,
-                                                         const SolveScalars *__restrict__ gate, CellMask mk) {
+                                                         const SolveScalars *__restrict__ gate, CellMask mk, UniformMatrix um) {
     if (gate && gate->done) return;
     __shared__ double red[32];
     const int W = dst.w, H = dst.h, pitch = dst.pitch;
@@ -69,28 +79,38 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
     if (in) {
         if (y0 > 0) {
             b_up = ld2(b.p + x + (size_t)(y0 - 1) * pitch);
-            ay_up = ld2(aPlusY.p + x + (size_t)(y0 - 1) * pitch);
+            if (!UNIFORM) ay_up = ld2(aPlusY.p + x + (size_t)(y0 - 1) * pitch);
         }
         b_c = ld2(b.p + x + (size_t)y0 * pitch);
     }
+    if (UNIFORM) ay_up = make_double2(um.off, um.off); // only used for y > 0, where the cell above has a lower neighbour
+    const int nx0 = (x > 0 ? 1 : 0) + (x < W - 1 ? 1 : 0), nx1 = 1 + (x + 1 < W - 1 ? 1 : 0); // x-neighbours of cells x, x+1
     double acc = 0.0;
     for (int y = y0; y < y1; y++) {
         const size_t row = (size_t)y * pitch;
         double2 ad = zero2, ax = zero2, ay = zero2;
         b_dn = zero2;
         if (in) {
-            ad = ld2(aDiag.p + x + row);
-            ax = ld2(aPlusX.p + x + row);
-            ay = ld2(aPlusY.p + x + row);
+            if (!UNIFORM) {
+                ad = ld2(aDiag.p + x + row);
+                ax = ld2(aPlusX.p + x + row);
+                ay = ld2(aPlusY.p + x + row);
+            }
             b_dn = ld2(b.p + x + row + pitch); // rows >= H are zero pad (allocation has 32 spare rows)
+        }
+        if (UNIFORM) {
+            const int ny = (y > 0 ? 1 : 0) + (y < H - 1 ? 1 : 0);
+            ad = make_double2(um.d[nx0 + ny], um.d[nx1 + ny]);
+            ax = make_double2(um.off, um.off); // every use below is guarded by the neighbour's existence
+            ay = ax;
         }
         // x-neighbours: b[x-1], aPlusX[x-1] from the lane to the left, b[x+2] from the right
         double b_l = __shfl_up_sync(0xffffffffu, b_c.y, 1);
-        double ax_l = __shfl_up_sync(0xffffffffu, ax.y, 1);
+        double ax_l = UNIFORM ? um.off : __shfl_up_sync(0xffffffffu, ax.y, 1);
         double b_r = __shfl_down_sync(0xffffffffu, b_c.x, 1);
         if (lane == 0 && x > 0 && in) {
             b_l = b.p[x - 1 + row];
-            ax_l = aPlusX.p[x - 1 + row];
+            if (!UNIFORM) ax_l = aPlusX.p[x - 1 + row];
         }
         if (lane == 31 && x + 2 < pitch) b_r = b.p[x + 2 + row];
 
@@ -343,14 +363,26 @@ static CellMask mask_of(ifl_ctx *c) {
 int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
     ProfScope ps_(c, IFL_K_MATVEC);
     dim3 g = vec_grid(dst);
-    if (with_dot) {
-        k_matvec<true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, partials_next(c), c->scal,
-                                                         mask_of(c));
-        c->n_partials = vec_blocks(dst);
-    } else {
-        k_matvec<false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, nullptr, nullptr,
-                                                          mask_of(c));
+    UniformMatrix um;
+    memset(&um, 0, sizeof um);
+    const bool uniform = c->matrix_uniform != 0;
+    if (uniform) { // the sums buildPressureMatrix forms: equal addends, so only their number matters
+        const double sc = c->matrix_scale;
+        um.d[0] = 0.0;
+        for (int n = 1; n <= 4; n++) um.d[n] = um.d[n - 1] + sc;
+        um.off = -sc;
     }
+    double *parts = with_dot ? partials_next(c) : nullptr;
+    SolveScalars *gate = with_dot ? c->scal : nullptr;
+    if (with_dot && uniform)
+        k_matvec<true, true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, parts, gate, mask_of(c), um);
+    else if (with_dot)
+        k_matvec<true, false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, parts, gate, mask_of(c), um);
+    else if (uniform)
+        k_matvec<false, true><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, parts, gate, mask_of(c), um);
+    else
+        k_matvec<false, false><<<g, VEC_THREADS, 0, c->stream>>>(dst, b, c->aDiag, c->aPlusX, c->aPlusY, parts, gate, mask_of(c), um);
+    if (with_dot) c->n_partials = vec_blocks(dst);
     IFL_LAUNCHED(c);
     return IFL_OK;
 }
