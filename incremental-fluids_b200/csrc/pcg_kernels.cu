@@ -84,8 +84,19 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
         b_c = ld2(b.p + x + (size_t)y0 * pitch);
     }
     if (UNIFORM) ay_up = make_double2(um.off, um.off); // only used for y > 0, where the cell above has a lower neighbour
+    // diagonals of cells x, x+1 for 0, 1, 2 vertical neighbours (selected once per thread; the loop only picks by row)
     const int nx0 = (x > 0 ? 1 : 0) + (x < W - 1 ? 1 : 0), nx1 = 1 + (x + 1 < W - 1 ? 1 : 0); // x-neighbours of cells x, x+1
+    double dx0[3], dx1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        dx0[k] = nx0 == 0 ? um.d[k] : (nx0 == 1 ? um.d[k + 1] : um.d[k + 2]);
+        dx1[k] = nx1 == 1 ? um.d[k + 1] : um.d[k + 2];
+    }
     double acc = 0.0;
+    // UNIFORM: one 16-byte load per row and thread is too little in flight to reach the HBM rate (measured 4.1 TB/s):
+    // the row after next is requested one iteration early
+    double2 b_dn2 = zero2;
+    if (UNIFORM && in) b_dn2 = ld2(b.p + x + (size_t)(y0 + 1) * pitch);
     for (int y = y0; y < y1; y++) {
         const size_t row = (size_t)y * pitch;
         double2 ad = zero2, ax = zero2, ay = zero2;
@@ -95,12 +106,15 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
                 ad = ld2(aDiag.p + x + row);
                 ax = ld2(aPlusX.p + x + row);
                 ay = ld2(aPlusY.p + x + row);
+                b_dn = ld2(b.p + x + row + pitch); // rows >= H are zero pad (allocation has 32 spare rows)
+            } else {
+                b_dn = b_dn2;
+                if (y + 1 < y1) b_dn2 = ld2(b.p + x + row + 2 * (size_t)pitch);
             }
-            b_dn = ld2(b.p + x + row + pitch); // rows >= H are zero pad (allocation has 32 spare rows)
         }
         if (UNIFORM) {
             const int ny = (y > 0 ? 1 : 0) + (y < H - 1 ? 1 : 0);
-            ad = make_double2(um.d[nx0 + ny], um.d[nx1 + ny]);
+            ad = make_double2(ny == 2 ? dx0[2] : (ny == 1 ? dx0[1] : dx0[0]), ny == 2 ? dx1[2] : (ny == 1 ? dx1[1] : dx1[0]));
             ax = make_double2(um.off, um.off); // every use below is guarded by the neighbour's existence
             ay = ax;
         }
