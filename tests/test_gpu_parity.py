@@ -402,3 +402,26 @@ def test_engine_variants_with_solids(ifl, monkeypatch, env):
     dev.applyPreconditioner("z", "r"); ref.call("applyPreconditioner", 2, 0)
     assert_bits(dev.get("z"), ref.buf("z"), "applyPreconditioner (masked)")
     dev.close(); ref.close()
+
+
+@pytest.mark.gpu
+def test_matvec_uses_an_uploaded_matrix(ifl, port):
+    """Chapter 3's k_matvec evaluates the matrix buildPressureMatrix wrote from the cell position; a matrix
+    the caller uploads afterwards must be READ again, and the next buildPressureMatrix re-enables the shortcut."""
+    w, h = 300, 140
+    dev, ora = make_pair(ifl, port, 3, w, h, seed=21)
+    rng = np.random.default_rng(22)
+    dev.buildPressureMatrix(0.005); ora.buildPressureMatrix(0.005)
+    sync_vec(dev, ora, "s", rng)
+    dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
+    assert_bits(dev.get("z"), ora.z, "matrixVectorProduct (position-only matrix)")
+    for name in ("aDiag", "aPlusX", "aPlusY"):
+        a = getattr(ora, name) * rng.uniform(0.5, 1.5, w * h)
+        getattr(ora, name)[:] = a
+        dev.set(name, a)
+    dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
+    assert_bits(dev.get("z"), ora.z, "matrixVectorProduct (uploaded matrix)")
+    dev.buildPressureMatrix(0.0025); ora.buildPressureMatrix(0.0025)
+    dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
+    assert_bits(dev.get("z"), ora.z, "matrixVectorProduct (rebuilt matrix)")
+    dev.close()
