@@ -249,6 +249,7 @@ static int create_ctx(ifl_ctx **out, int w, int h, int version, int device, int 
         Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
         const int ncells = pcg_chapter(c) ? 11 : 2; // chapters 1-2 only own _r and _p (v2:219-220)
         for (int i = 0; i < ncells && rc == IFL_OK; i++) rc = alloc_arr(c, *cells[i], w, h);
+        if (rc == IFL_OK && version == 3) rc = alloc_arr(c, c->s2, w, h); // ping-pong partner of s (pcg_kernels.cu: k_xpay_matvec)
         if (rc != IFL_OK) break;
         // two partial buffers (reductions alternate, pcg_kernels.cu); with several ranks they are
         // rank 0's memory and every rank folds all of them
@@ -311,6 +312,7 @@ int ifl_destroy(ifl_ctx *c) {
     if (c->ext_ready) cudaFree(c->ext_ready);
     Arr *cells[] = {&c->r, &c->p, &c->z, &c->s, &c->q, &c->precon, &c->aDiag, &c->aPlusX, &c->aPlusY, &c->cx, &c->cy};
     for (int i = 0; i < 11; i++) free_arr(c, *cells[i]);
+    free_arr(c, c->s2);
     if (c->partials_buf[0]) dist_free_mem(c, c->partials_buf[0]);
     if (c->scal) cudaFree(c->scal);
     if (c->scal_h) cudaFreeHost(c->scal_h);

@@ -93,6 +93,8 @@ struct ifl_ctx {
     cudaStream_t stream;
     ifl::Field fd[4]; // d, u, v, t
     ifl::Arr r, p, z, s, q, precon, aDiag, aPlusX, aPlusY, cx, cy;
+    ifl::Arr s2;                       // chapter 3: the other half of the search direction's ping-pong pair (k_xpay_matvec)
+    int fuse_xpay, xpay_pending, xpay_fused; // IFL_FUSE_XPAY; s = z + beta s waits for the next matvec; fused launches of this solve
     ifl::Arr pe;    // chapters 4+: precon with +0.0 at non-fluid cells (what the masked sweeps multiply by)
     ifl::Arr fmask; // chapters 4+: 1.0 at fluid cells of _d, 0.0 elsewhere (operand of the masked factorisation)
     ifl::Arr uDensity, vDensity; // chapter 7+: densities on the staggered faces (v7:598-599)

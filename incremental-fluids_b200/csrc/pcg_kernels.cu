@@ -161,6 +161,82 @@ __global__ void __launch_bounds__(VEC_THREADS) k_matvec(Arr dst, Arr b, Arr aDia
     }
 }
 
+// Chapter 3, fused: s' = z + beta*s (v3:375 of the PREVIOUS iteration) ; q = A*s' ; partial[block] = sum(q*s')  (v3:361-362).
+// The block forms s' for its 16 rows and for the row above and below them in registers (x-neighbours by shuffle), so the
+// search direction is read once instead of written, read and re-read: 34 instead of 24 + 16 bytes per cell.  s' goes to the
+// OTHER buffer of a ping-pong pair -- in place, a block could find its halo rows already overwritten by its neighbours --
+// and the host swaps the two Arr records after the launch.  Same products, same order as k_scaled_add + k_matvec<UNIFORM>.
+__global__ void __launch_bounds__(VEC_THREADS) k_xpay_matvec(Arr dst, Arr z, Arr s_old, Arr s_new, double *__restrict__ partials,
+                                                              const SolveScalars *__restrict__ sc, UniformMatrix um) {
+    if (sc->done) return;
+    __shared__ double red[32];
+    const double beta = sc->beta;
+    const int W = dst.w, H = dst.h, pitch = dst.pitch;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * VEC_COLS + threadIdx.x * 2;
+    const int y0 = dst.ry0 + blockIdx.y * VEC_ROWS;
+    const int y1 = imin(y0 + VEC_ROWS, dst.ry1);
+    const bool in = x < pitch; // may load (pad columns are zero)
+    const double2 zero2 = make_double2(0.0, 0.0);
+    auto xpay2 = [&](size_t i) { // s' of cells i, i+1 (pad cells: 0 + 0*beta)
+        const double2 zv = ld2(z.p + i), sv = ld2(s_old.p + i);
+        return make_double2(zv.x + sv.x * beta, zv.y + sv.y * beta);
+    };
+    auto xpay1 = [&](size_t i) { return z.p[i] + s_old.p[i] * beta; };
+
+    double2 b_up = zero2, b_c = zero2, b_dn = zero2;
+    if (in) {
+        if (y0 > 0) b_up = xpay2(x + (size_t)(y0 - 1) * pitch);
+        b_c = xpay2(x + (size_t)y0 * pitch);
+    }
+    const int nx0 = (x > 0 ? 1 : 0) + (x < W - 1 ? 1 : 0), nx1 = 1 + (x + 1 < W - 1 ? 1 : 0); // x-neighbours of cells x, x+1
+    double dx0[3], dx1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        dx0[k] = nx0 == 0 ? um.d[k] : (nx0 == 1 ? um.d[k + 1] : um.d[k + 2]);
+        dx1[k] = nx1 == 1 ? um.d[k + 1] : um.d[k + 2];
+    }
+    const double off = um.off;
+    double acc = 0.0;
+    for (int y = y0; y < y1; y++) {
+        const size_t row = (size_t)y * pitch;
+        b_dn = zero2;
+        if (in && y + 1 < H) b_dn = xpay2(x + row + pitch); // (row H is a zero pad row and never multiplied)
+        const int ny = (y > 0 ? 1 : 0) + (y < H - 1 ? 1 : 0);
+        const double2 ad = make_double2(ny == 2 ? dx0[2] : (ny == 1 ? dx0[1] : dx0[0]), ny == 2 ? dx1[2] : (ny == 1 ? dx1[1] : dx1[0]));
+        double b_l = __shfl_up_sync(0xffffffffu, b_c.y, 1);
+        double b_r = __shfl_down_sync(0xffffffffu, b_c.x, 1);
+        if (lane == 0 && x > 0 && in) b_l = xpay1(x - 1 + row);
+        if (lane == 31 && x + 2 < pitch) b_r = xpay1(x + 2 + row);
+
+        double t0 = ad.x * b_c.x;
+        if (x > 0) t0 += off * b_l;
+        if (y > 0) t0 += off * b_up.x;
+        if (x < W - 1) t0 += off * b_c.y;
+        if (y < H - 1) t0 += off * b_dn.x;
+        double t1 = ad.y * b_c.y;
+        t1 += off * b_c.x;
+        if (y > 0) t1 += off * b_up.y;
+        if (x + 1 < W - 1) t1 += off * b_r;
+        if (y < H - 1) t1 += off * b_dn.y;
+
+        if (x + 1 < W) {
+            st2(s_new.p + x + row, b_c);
+            st2(dst.p + x + row, make_double2(t0, t1));
+            acc += t0 * b_c.x;
+            acc += t1 * b_c.y;
+        } else if (x < W) {
+            st2(s_new.p + x + row, b_c); // (the pad cell next to the last column receives 0 + 0*beta, as k_scaled_add writes it)
+            dst.p[x + row] = t0;
+            acc += t0 * b_c.x;
+        }
+        b_up = b_c;
+        b_c = b_dn;
+    }
+    const double sum = block_reduce<false>(acc, red);
+    if (threadIdx.x == 0) partials[(y0 / VEC_ROWS) * gridDim.x + blockIdx.x] = sum;
+}
+
 // p += alpha*s ; r += q*(-alpha) ; partial[block] = max|r|     v3:363-366
 // band_count (may be null): one counter per band of 64 rows; every block adds 1 to its band's counter after its
 // stores, so that the forward sweep -- launched concurrently on the main stream -- can start a strip as soon as
@@ -401,6 +477,23 @@ int launch_matvec(ifl_ctx *c, const Arr &dst, const Arr &b, bool with_dot) {
     return IFL_OK;
 }
 
+// chapter 3: the pending s = z + beta*s of the previous iteration folded into q = A*s (ping-pong pair s / s2)
+static int launch_xpay_matvec(ifl_ctx *c) {
+    ProfScope ps_(c, IFL_K_MATVEC);
+    UniformMatrix um;
+    memset(&um, 0, sizeof um);
+    const double sc = c->matrix_scale;
+    for (int n = 1; n <= 4; n++) um.d[n] = um.d[n - 1] + sc;
+    um.off = -sc;
+    k_xpay_matvec<<<vec_grid(c->q), VEC_THREADS, 0, c->stream>>>(c->q, c->z, c->s, c->s2, partials_next(c), c->scal, um);
+    c->n_partials = vec_blocks(c->q);
+    IFL_LAUNCHED(c);
+    Arr t = c->s; // the other buffer now holds s
+    c->s = c->s2;
+    c->s2 = t;
+    return IFL_OK;
+}
+
 int launch_dot(ifl_ctx *c, const Arr &a, const Arr &b) {
     ProfScope ps_(c, IFL_K_SCALAR);
     k_reduce2<false><<<vec_grid(a), VEC_THREADS, 0, c->stream>>>(a, b, partials_next(c), mask_of(c));
@@ -460,7 +553,13 @@ static int scalar_stage(ifl_ctx *c) {
 
 // One PCG iteration, enqueued without any host synchronisation (v3:361-376).
 static int enqueue_iteration(ifl_ctx *c) {
-    IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
+    if (c->xpay_pending) { // chapter 3: s = z + beta s of the previous iteration rides on this matvec
+        IFL_TRY(launch_xpay_matvec(c));
+        c->xpay_fused++;
+        c->xpay_pending = 0;
+    } else {
+        IFL_TRY(launch_matvec(c, c->q, c->s, true)); // q = A s ; partial q.s
+    }
     IFL_TRY(scalar_stage<SC_ALPHA>(c));
     // Only while the sweep leaves at least half of the SMs free.  A sweep CTA takes its SM's whole shared-memory
     // carve-out and the streaming kernel's CTAs do not become resident next to it, so the streaming kernel runs on the
@@ -510,12 +609,14 @@ static int enqueue_iteration(ifl_ctx *c) {
     }
     IFL_TRY(launch_precon_backward(c, c->z, c->r, true, true)); // partial z.r
     IFL_TRY(scalar_stage<SC_BETA>(c));
-    {
+    if (c->matrix_uniform && c->fuse_xpay && c->s2.p) {
+        c->xpay_pending = 1; // folded into the next iteration's matvec (or flushed at the end of the solve)
+    } else {
         ProfScope ps_(c, IFL_K_XPAY);
         k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, c->stream>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
         IFL_LAUNCHED(c);
     }
-    return dist_barrier(c, true); // the next matvec reads the neighbours' boundary rows of s
+    return dist_barrier(c, true); // the next matvec reads the neighbours' boundary rows of s (fused: of z)
 }
 
 int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
@@ -529,6 +630,8 @@ int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
     // for the side stream before every convergence test, and drains at the end of a solve)
     IFL_CUDA(cudaMemsetAsync(c->band_count, 0, (size_t)((c->H + 63) / 64 + 1) * sizeof(unsigned), st));
     c->band_epoch = 0;
+    c->xpay_pending = 0;
+    c->xpay_fused = 0;
     IFL_CUDA(cudaMemsetAsync((char *)c->p.p + c->p.own_begin(), 0, c->p.own_end() - c->p.own_begin(), st));
     IFL_TRY(dist_barrier(c, false)); // the upstream slab's last row of cy (factorisation) is final
     IFL_TRY(launch_precon_forward(c, c->z, c->r, false));
@@ -587,6 +690,13 @@ int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
         head ^= 1;
         pending--;
     }
+    if (rc == IFL_OK && c->xpay_pending) { // the last iteration's s = z + beta s (a no-op launch once the solve has converged)
+        ProfScope ps_(c, IFL_K_XPAY);
+        k_scaled_add<true><<<vec_grid(c->s), VEC_THREADS, 0, st>>>(c->s, c->z, c->s, 0.0, c->scal, mask_of(c));
+        IFL_LAUNCHED(c);
+        c->xpay_pending = 0;
+        pending = imax(pending, 1);
+    }
     if (pending > 0 && cudaStreamSynchronize(st) != cudaSuccess && rc == IFL_OK) { // drain gated no-op launches
         set_error("pcg_project: %s", cudaGetErrorString(cudaGetLastError()));
         rc = IFL_E_CUDA;
@@ -594,6 +704,15 @@ int pcg_project(ifl_ctx *c, int limit, ifl_solve_info *info) {
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
     if (rc != IFL_OK) return rc;
+    {   // every fused launch swapped the s / s2 records on the host; the launches enqueued after convergence were gated
+        // off on the device, so an odd number of them leaves the records pointing the wrong way round
+        const int executed = last.done == 1 ? imin(last.iter, c->xpay_fused) : (last.done == 2 ? 0 : c->xpay_fused);
+        if ((c->xpay_fused - executed) & 1) {
+            Arr t = c->s;
+            c->s = c->s2;
+            c->s2 = t;
+        }
+    }
     if (info) {
         info->max_error = last.max_error;
         if (last.done == 2) {

@@ -873,6 +873,8 @@ int sweep_init(ifl_ctx *c) {
     // tri_kernels.cu goes to the non-portable cluster size 16 when every strip of the sweep is resident at once
     // (4096^2: 4 clusters instead of 8, 440 instead of 453 us per sweep, 1.140 instead of 1.163 ms per PCG iteration;
     // profiles/r02_tri_experiments.txt section 10).  IFL_TRI_CLUSTER16=0 keeps 8.
+    c->fuse_xpay = 1;
+    if (const char *e = getenv("IFL_FUSE_XPAY")) c->fuse_xpay = atoi(e) != 0;
     c->matvec_uniform_allowed = 1;
     if (const char *e = getenv("IFL_MATVEC_UNIFORM")) c->matvec_uniform_allowed = atoi(e) != 0;
     c->tri_cluster16 = 1;

@@ -425,3 +425,23 @@ def test_matvec_uses_an_uploaded_matrix(ifl, port):
     dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
     assert_bits(dev.get("z"), ora.z, "matrixVectorProduct (rebuilt matrix)")
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limit", [1, 2, 3, 4, 9, 400])
+def test_solver_vectors_after_project(ifl, port, limit):
+    """r, z, s and p as the reference leaves them when the budget runs out after `limit` iterations or the solve
+    converges (limit 400: after 35 at this size) -- chapter 3 keeps s in a ping-pong pair whose halves are swapped once
+    per fused launch, an odd and an even number of times here."""
+    w, h = 200, 136
+    dev, ora = make_pair(ifl, port, 3, w, h, seed=31)
+    for s in (dev, ora):
+        s.buildRhs(); s.buildPressureMatrix(0.005); s.buildPreconditioner()
+    sd, so = dev.project(limit), ora.project(limit)
+    assert sd[:2] == so[:2], (sd, so)
+    for name in ("r", "z", "s", "p"):
+        assert rel_err(dev.get(name), getattr(ora, name)) <= 1e-9, (limit, name)
+    # and the granular entry points keep working on the buffer that now is `s`
+    dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
+    assert rel_err(dev.get("z"), ora.z) <= 1e-9
+    dev.close()
