@@ -431,15 +431,21 @@ def test_matvec_uses_an_uploaded_matrix(ifl, port):
 @pytest.mark.parametrize("limit", [1, 2, 3, 4, 9, 400])
 def test_solver_vectors_after_project(ifl, port, limit):
     """r, z, s and p as the reference leaves them when the budget runs out after `limit` iterations or the solve
-    converges (limit 400: after 35 at this size) -- chapter 3 keeps s in a ping-pong pair whose halves are swapped once
-    per fused launch, an odd and an even number of times here."""
+    converges (limit 400) -- chapter 3 keeps s in a ping-pong pair whose halves are swapped once per fused launch
+    (DESIGN 3.2), an odd and an even number of times here."""
     w, h = 200, 136
-    dev, ora = make_pair(ifl, port, 3, w, h, seed=31)
+    dev = ifl.FluidSolver(w, h, 0.1, version=3)
+    ora = port.PortSolver(3, w, h, 0.1)
+    inflow = (0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)
     for s in (dev, ora):
+        s.addInflow(*inflow)
         s.buildRhs(); s.buildPressureMatrix(0.005); s.buildPreconditioner()
     sd, so = dev.project(limit), ora.project(limit)
     assert sd[:2] == so[:2], (sd, so)
-    for name in ("r", "z", "s", "p"):
+    converged = sd[0] == 0
+    assert converged == (limit == 400), sd
+    # (a converged reference solve returns with A*s still in _z, v3:361-368: the device keeps that product in `q`)
+    for name in ("r", "s", "p") if converged else ("r", "z", "s", "p"):
         assert rel_err(dev.get(name), getattr(ora, name)) <= 1e-9, (limit, name)
     # and the granular entry points keep working on the buffer that now is `s`
     dev.matrixVectorProduct("z", "s"); ora.matrixVectorProduct(ora.z, ora.s)
