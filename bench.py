@@ -62,7 +62,7 @@ DT, DENSITY, LIMIT = 0.005, 0.1, 600              # v3:473-474, v3:437
 ALG_BYTES = {"matvec": 40, "axpy2_norm": 48, "precon_fwd": 40, "precon_bwd": 48, "xpay": 24,
              "advect": 80.0 / 3, "factor": 32, "gs_sweep": 24}
 # the kernel behind each class (as launched by ifl_project), for the ncu traffic lookup
-KERNEL_OF = {"precon_fwd": "k_tri<0,0,0>", "precon_bwd": "k_tri<1,1,0>", "matvec": "k_matvec<1,1>",
+KERNEL_OF = {"precon_fwd": "k_tri<0,0,0>", "precon_bwd": "k_tri<1,1,0>", "matvec": "k_xpay_matvec",
              "axpy2_norm": "k_axpy2_norm", "xpay": "k_scaled_add<1>", "gs_sweep": "k_sweep<3,0,0>"}
 
 

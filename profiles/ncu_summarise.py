@@ -31,7 +31,7 @@ WANT = {
     "launch__block_size": "block",
 }
 # algorithmic bytes per cell of the kernels that have one; the grid is given per report
-ALG = {"k_tri<0": 40, "k_tri<1": 48, "k_matvec": 40, "k_axpy2_norm": 48, "k_scaled_add": 24, "k_advect": 80.0 / 3,
+ALG = {"k_tri<0": 40, "k_tri<1": 48, "k_matvec": 40, "k_xpay_matvec": 64, "k_axpy2_norm": 48, "k_scaled_add": 24, "k_advect": 80.0 / 3,
        "k_sweep<2": 32, "k_sweep<4": 32, "k_sweep<3": 24, "k_build_rhs": 24, "k_build_matrix": 24, "k_apply_pressure": 24}
 CELLS = {"gs_sweep": 2048 * 2048, "p2g": 1024 * 1024, "g2p": 1024 * 1024, "padvect": 1024 * 1024}
 
@@ -103,7 +103,7 @@ for r in rows:
         fmt(r.get("fp64_pipe_pct") if r.get("fp64_pipe_pct") is not None else r.get("fp64_inst_pct")), fmt(r.get("issue_active_pct")),
         fmt(r.get("smem_bank_conflicts"), "%d")))
     name = short.replace("(bool)", "").replace("(int)", "").replace(" ", "")
-    if r["report"] in ("tri", "matvec", "axpy2_norm", "scaled_add"):
+    if r["report"] in ("tri", "matvec", "xpay_matvec", "axpy2_norm", "scaled_add"):
         traffic["bytes_per_launch"][name] = dram
 with open(os.path.join(ROOT, "profiles", "r02_ncu_kernel_table.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
