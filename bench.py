@@ -18,12 +18,15 @@ v3:433-447, constants v3:470-486).  --config selects the other BASELINE.json wor
 
 metric   cell-updates/s = S*S*steps / time         (device-resident fields: `value`, profiling OFF)
 e2e      same metric through the host-buffer path: every step uploads d,u,v from pinned
-         host memory, runs the step and downloads d,u,v (timed region includes copies)
+         host memory, runs the step and downloads d,u,v (timed region includes copies); chapter 8, whose
+         update() stamps its own inflow and whose particles live in the solver as in the reference, reads back
+         the two fields main() renders (d, T) every step
 roofline a SEPARATE profiled pass (per-kernel-class CUDA events, ifl_profile) after the timed region:
          the dominant class' algorithmic bytes / its mean launch time vs the measured HBM copy
          bandwidth in MEASURED_PEAKS.json; `traffic` from the committed ncu capture of that kernel
 cpu_baseline  the reference's own CPU code (oracle/_ref if built, else the C port) on
-         one host core, bounded sample, extrapolated per step (stated in `sample`)
+         one host core, bounded sample, extrapolated per step (stated in `sample`): everything update() does
+         outside the pressure solve's iterations once in full, then a few iterations timed
 headline workload only:
 pcg_to_tolerance   one solve from the plume state with the cap lifted: iterations and time to |r|inf < 1e-5
 strong_16384       the north-star grid, 16384^2, on the N GPUs of this run (2 steps) and -- N > 1 -- on rank 0
