@@ -48,3 +48,18 @@ def test_weak_scaling_grid_sides():
     assert [bench.grid_side(A, n) for n in (1, 2, 4, 8)] == [4096, 5792, 8192, 11584]
     A.size = 16384
     assert bench.grid_side(A, 8) == 16384
+
+
+@pytest.mark.parametrize("config", ["3", "4", "5"])
+def test_reference_arm_samples_a_live_solve(config):
+    """Chapters 5-8: the sampled PCG iterations must belong to a solve with a non-trivial right-hand side (chapters 6+
+    get theirs from the buoyancy of the heat step: without it project() returns at once and the extrapolated CPU time
+    collapses -- the sampler therefore replays update() up to the pressure solve, v7:1120-1147, v8:1350-1385)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_v%s.so" % {"3": 5, "4": 7, "5": 8}[config])):
+        pytest.skip("oracle/_ref not built")
+    out = run(None, "--config", config, "--size", "96", "--steps", "1", "--warmup", "0")
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    # 96^2 cells, >= 10 sampled iterations extrapolated to hundreds: a live solve stays far below 1e6 cell-updates/s
+    assert 1e3 < line["value"] < 3e5, line["value"]
+    assert "extrapolated to the" in line["cpu_baseline"]["sample"]
